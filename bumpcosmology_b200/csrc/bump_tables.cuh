@@ -1,0 +1,340 @@
+// Prologue: theta-dependent tables with forward-mode tangents, one launch.
+//
+//   blocks 0..NM-1 : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
+//   block  NM      : flat wCDM distance tables        (intensity_models.py:229-235 + utils.py:3-8 cumtrapz)
+//   last block to finish (atomic ticket): scalars (intensity_models.py:134-138,167-168) and the packed
+//   per-bin records the streaming kernel bulk-copies into shared memory.
+#pragma once
+#include "bump_dual.cuh"
+#include "bump_layout.cuh"
+
+namespace bump {
+
+// aux (global) workspace layout, doubles: raw knots and tangents (also what bump_debug_tables exposes)
+constexpr int AUX_ZG = 0;                       // [NZ]
+constexpr int AUX_DL = AUX_ZG + NZ;             // [NZ]
+constexpr int AUX_DDL = AUX_DL + NZ;            // [NZ]
+constexpr int AUX_DVC = AUX_DDL + NZ;           // [NZ]
+constexpr int AUX_TAN = AUX_DVC + NZ;           // [3 tables: dl, ddl, dvc][3 params: Om, w, wa][NZ]
+constexpr int AUX_G = AUX_TAN + 9 * NZ;         // [6][NM]: log_dN_grid, d/d(a, b, mpisn, mbhmax, sigma)
+constexpr int AUX_DOUBLES = AUX_G + 6 * NM;
+
+constexpr int PRO_THREADS = 256;
+
+// Read-only view that always loads through L2 (the data were produced by other CTAs of the same launch).
+struct CgView {
+    const double* p;
+    __device__ __forceinline__ double operator[](int i) const { return __ldcg(p + i); }
+    __device__ __forceinline__ CgView operator+(int o) const { return CgView{p + o}; }
+};
+
+struct EvalConsts {   // theta-independent numbers the prologue copies into the scalar block
+    double log_nsamp;
+    double log_ndraw;
+    double nobs_local;
+    int use_wa;
+};
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red /* >= 8*NV doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < PRO_THREADS / 32; ++w) s += red[w * NV + k];
+        v[k] = s;
+    }
+}
+
+__device__ __forceinline__ double block_max(double x, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    double m = red[0];
+    for (int w = 1; w < PRO_THREADS / 32; ++w) m = fmax(m, red[w]);
+    return m;
+}
+
+// ---------------------------------------------------------------- PISN row (Dual<5>: a, b, mpisn, mbhmax, sigma)
+__device__ void pisn_row(const double* __restrict__ th, int i, double* __restrict__ aux, double* sm) {
+    typedef Dual<5> D;
+    const int j = threadIdx.x;
+    D a = D::var(th[T_A], 0), b = D::var(th[T_B], 1), mpisn = D::var(th[T_MPISN], 2),
+      M = D::var(th[T_MBHMAX], 3), sg = D::var(th[T_SIGMA], 4);
+    D top = M + 7.0 * sg;                                 // :99
+    D mcomax = 2.0 * M - mpisn;                           // :29
+    D mco_top = mcomax + dsqrt(4.0 * M * (M - mpisn));    // :30
+    const double si = (double)i / (NM - 1), sj = (double)j / (NM - 1);
+    D mbh = (i == NM - 1) ? top : (MIN_BH_MASS * (1.0 - si) + top * si);        // :102 linspace
+    D mco = (j == NM - 1) ? mco_top : (MIN_CO_MASS * (1.0 - sj) + mco_top * sj); // :103
+    D alpha = 1.0 / (4.0 * (mpisn - M));                  // :22
+    D mu = (mco.v < mpisn.v) ? mco : (M + alpha * dsquare(mco - mcomax));        // :25
+    D lx = dlog(mco / MTR);
+    D ell = (mco.v < MTR) ? (-a * lx) : (-b * lx);        // :43
+    D u = (mbh - mu) / sg;
+    D lw = ell - 0.5 * dsquare(u) - HALF_LOG_2PI - dlog(sg);   // :105
+
+    // neighbour exchange through shared memory: sm[0..6*NM) = lw (v, d[5]); sm[6*NM..) = mco (v, d_mpisn, d_mbhmax)
+    double* s_lw = sm;
+    double* s_mco = sm + 6 * NM;
+    s_lw[j] = lw.v;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s_lw[(k + 1) * NM + j] = lw.d[k];
+    s_mco[j] = mco.v;
+    s_mco[NM + j] = mco.d[2];
+    s_mco[2 * NM + j] = mco.d[3];
+    __syncthreads();
+    D term(-INFINITY);
+    if (j < NM - 1) {
+        D lw1;
+        lw1.v = s_lw[j + 1];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) lw1.d[k] = s_lw[(k + 1) * NM + j + 1];
+        D dm(s_mco[j + 1] - mco.v);
+        dm.d[2] = s_mco[NM + j + 1] - mco.d[2];
+        dm.d[3] = s_mco[2 * NM + j + 1] - mco.d[3];
+        term = dlogaddexp(lw1, lw) + dlog(dm) - LN2;      // :106  log(0.5) + logaddexp + log(diff)
+    }
+    double* red = sm + 9 * NM;
+    const double mx = block_max(term.v, red);             // :107  logsumexp over the 255 cells
+    double acc[6];
+    const double e = (j < NM - 1) ? exp(term.v - mx) : 0.0;
+    acc[0] = e;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k + 1] = (j < NM - 1) ? e * term.d[k] : 0.0;
+    block_sum<6>(acc, red);
+    if (j == 0) {
+        aux[AUX_G + i] = mx + log(acc[0]);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) aux[AUX_G + (k + 1) * NM + i] = acc[k + 1] / acc[0];
+    }
+}
+
+// ---------------------------------------------------------------- cosmology tables (Dual<3>: Om, w, wa)
+__device__ void cosmology_tables(const double* __restrict__ th, int use_wa, double* __restrict__ aux, double* sm) {
+    typedef Dual<3> D;
+    const int tid = threadIdx.x;
+    const double h = th[T_H];
+    D Om = D::var(th[T_OM], 0), w = D::var(th[T_W], 1), wa = D::var(use_wa ? th[T_WA] : 0.0, 2);
+    const double dH = C_H100_GPC / h;   // :239
+    constexpr int PER = NZ / PRO_THREADS;  // 4 knots per thread
+    double z[PER + 1];
+    D iE[PER + 1];
+#pragma unroll
+    for (int q = 0; q <= PER; ++q) {
+        const int k = tid * PER + q;
+        const double lz = (k >= NZ - 1) ? LOG_ZMAX1 : k * ZSTEP;   // np.linspace(0, log(101), 1024), :230
+        z[q] = expm1(lz);
+        const double opz = 1.0 + z[q];
+        const double lopz = log(opz);
+        D de = dexp((3.0 * (1.0 + w + wa)) * lopz);               // opz**(3(1+w)), :256
+        if (use_wa) de = de * dexp(wa * (-3.0 * z[q] / opz));     // CPL extension (no reference counterpart)
+        D E = dsqrt(Om * (opz * opz * opz) + (1.0 - Om) * de);
+        iE[q] = 1.0 / E;
+    }
+    // per-thread increments of the cumulative trapezoid (utils.py:8), then a block-wide exclusive scan
+    D inc[PER];
+    D tot(0.0);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int k = tid * PER + q;
+        inc[q] = (k < NZ - 1) ? (0.5 * (z[q + 1] - z[q])) * (iE[q] + iE[q + 1]) : D(0.0);
+        tot = tot + inc[q];
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    double sc[4] = {tot.v, tot.d[0], tot.d[1], tot.d[2]};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double n = __shfl_up_sync(0xffffffffu, sc[c], o);
+            if (lane >= o) sc[c] += n;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm[warp * 4 + c] = sc[c];
+    }
+    __syncthreads();
+    double base[4] = {0, 0, 0, 0};
+    for (int ww = 0; ww < warp; ++ww) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base[c] += sm[ww * 4 + c];
+    }
+    D C;  // exclusive prefix for this thread's first knot
+    C.v = base[0] + sc[0] - tot.v;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C.d[c] = base[c + 1] + sc[c + 1] - tot.d[c];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int k = tid * PER + q;
+        const double opz = 1.0 + z[q];
+        D dc = dH * C;                                        // :231
+        D dl = dc * opz;                                      // :232
+        D ddl = dc + (dH * opz) * iE[q];                      // :233
+        D dvc = (FOUR_PI * dH) * (dsquare(dc) * iE[q]);       // :235
+        aux[AUX_ZG + k] = z[q];
+        aux[AUX_DL + k] = dl.v;
+        aux[AUX_DDL + k] = ddl.v;
+        aux[AUX_DVC + k] = dvc.v;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            aux[AUX_TAN + (0 * 3 + c) * NZ + k] = dl.d[c];
+            aux[AUX_TAN + (1 * 3 + c) * NZ + k] = ddl.d[c];
+            aux[AUX_TAN + (2 * 3 + c) * NZ + k] = dvc.d[c];
+        }
+        C = C + inc[q];
+    }
+}
+
+// ---------------------------------------------------------------- scalars (Dual<7>: a, b, c, mpisn, mbhmax, sigma, fpl)
+__device__ void build_scalars(const double* th, const double* aux_, const EvalConsts ec, double* scal) {
+    const CgView aux{aux_};   // written by other blocks of this launch: read through L2 (ld.global.cg)
+    typedef Dual<7> D;
+    const int map5[5] = {0, 1, 3, 4, 5};   // (a, b, mpisn, mbhmax, sigma) -> slots of Dual<7>
+    D c = D::var(th[T_C], 2), M = D::var(th[T_MBHMAX], 4), sg = D::var(th[T_SIGMA], 5), fpl = D::var(th[T_FPL], 6);
+    D top = M + 7.0 * sg;
+    auto knot = [&](int k) -> D {
+        const double s = (double)k / (NM - 1);
+        return (k == NM - 1) ? top : (MIN_BH_MASS * (1.0 - s) + top * s);
+    };
+    auto Gk = [&](int k) -> D {
+        D g(aux[AUX_G + k]);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) g.d[map5[q]] = aux[AUX_G + (q + 1) * NM + k];
+        return g;
+    };
+    // jnp.interp(m, mbh_grid, log_dN_grid), differentiable in m, the knots and the values (:110-111)
+    auto pisn = [&](const D& m) -> D {
+        int i = (int)floor((m.v - MIN_BH_MASS) / (top.v - MIN_BH_MASS) * (NM - 1)) + 1;
+        i = min(max(i, 1), NM - 1);
+        while (i < NM - 1 && knot(i).v <= m.v) ++i;       // i = clip(#{knots <= m}, 1, n-1)
+        while (i > 1 && knot(i - 1).v > m.v) --i;
+        D x0 = knot(i - 1), x1 = knot(i), f0 = Gk(i - 1), f1 = Gk(i);
+        D f = f0 + ((m - x0) / (x1 - x0)) * (f1 - f0);
+        if (m.v < knot(0).v) f = Gk(0);
+        if (m.v > top.v) f = Gk(NM - 1);
+        return f;
+    };
+    D lpn = dlog(fpl) + pisn(M);                                   // :136
+    // log_norm = -(self(mref) + log(mref)) with log_norm = 0 inside (:138, :140-151)
+    D mref(MREF);
+    D P = (MREF <= MIN_BH_MASS || MREF >= top.v) ? D(-INFINITY) : pisn(mref);
+    D turn = LN2 - dlog1p(dexp(-(mref - M) / (M * TURNON_WIDTH)));  // :52-54
+    D Q = -c * dlog(mref / M) + lpn + turn;
+    D A0 = (MREF < MBH_MIN) ? D(-INFINITY) : dlogaddexp(P, Q);
+    D ln = -(A0 + log(MREF));
+    // rate normalisation: log_norm = -self(zref=0) (:168,173)
+    const double kappa = th[T_KAPPA], zp = th[T_ZP];
+    const double lopzp = log1p(zp);
+    const double r0 = exp(-kappa * lopzp);
+    const double lnV = log1p(r0);
+    const double sig0 = r0 / (1.0 + r0);
+
+    scal[S_H] = th[T_H];
+    scal[S_INV_H] = 1.0 / th[T_H];
+    scal[S_C] = th[T_C];
+    scal[S_M] = M.v;
+    scal[S_LOG_M] = log(M.v);
+    scal[S_INV_DM] = 1.0 / (M.v * TURNON_WIDTH);
+    scal[S_LPN] = lpn.v;
+    scal[S_TOP] = top.v;
+    scal[S_INV_DMBH] = (NM - 1) / (top.v - MIN_BH_MASS);
+    scal[S_INV_TOPM3] = 1.0 / (top.v - MIN_BH_MASS);
+    scal[S_BETA] = th[T_BETA];
+    scal[S_LAM] = th[T_LAM];
+    scal[S_KAPPA] = kappa;
+    scal[S_ZP] = zp;
+    scal[S_LOPZP] = lopzp;
+    scal[S_DL_LAST] = aux[AUX_DL + NZ - 1];
+    scal[S_FPL] = fpl.v;
+    scal[S_CONST] = 2.0 * ln.v + lnV - th[T_BETA] * LOG_MREF_PAIR;
+    scal[S_LOG_NORM] = ln.v;
+    scal[S_RATE_LOG_NORM] = lnV;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) scal[S_LPN_D0 + q] = lpn.d[map5[q]];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) scal[S_LN_D0 + q] = ln.d[q];
+    scal[S_LNV_KAPPA] = -sig0 * lopzp;
+    scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
+    scal[S_LOG_NSAMP] = ec.log_nsamp;
+    scal[S_LOG_NDRAW] = ec.log_ndraw;
+    scal[S_NOBS_LOCAL] = ec.nobs_local;
+}
+
+__device__ void build_records(const double* aux_, int use_wa, double* blob) {
+    const CgView aux{aux_};
+    double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
+    double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
+    double* dlk = blob + OFF_DLK;
+    for (int b = threadIdx.x; b < NZ; b += blockDim.x) {
+        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // bin NZ-1 is padding (copy of the last bin)
+        const CgView dl = aux + AUX_DL;
+        cos[CR_DL * NZ + b] = make_double2(dl[b0], 1.0 / (dl[b1] - dl[b0]));
+        const CgView dvc = aux + AUX_DVC;
+        cos[CR_DVC * NZ + b] = make_double2(dvc[b0], dvc[b1] - dvc[b0]);
+        const CgView ddl = aux + AUX_DDL;
+        cos[CR_DDL * NZ + b] = make_double2(ddl[b0], ddl[b1] - ddl[b0]);
+        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa]
+        const int recs[6] = {CR_DL_OM, CR_DL_W, CR_DDL_OM, CR_DDL_W, CR_DVC_OM, CR_DVC_W};
+        const int srcs[6] = {0 * 3 + 0, 0 * 3 + 1, 1 * 3 + 0, 1 * 3 + 1, 2 * 3 + 0, 2 * 3 + 1};
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const CgView t = aux + (AUX_TAN + srcs[r] * NZ);
+            cos[recs[r] * NZ + b] = make_double2(t[b0], t[b1] - t[b0]);
+        }
+        const double lz = (b0 >= NZ - 1) ? LOG_ZMAX1 : b0 * ZSTEP;
+        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), lz);
+        dlk[b] = dl[b];
+    }
+    for (int b = threadIdx.x; b < NM; b += blockDim.x) {
+        const int b0 = min(b, NM - 2), b1 = b0 + 1;
+#pragma unroll
+        for (int r = 0; r < NMREC; ++r) {
+            const CgView g = aux + (AUX_G + r * NM);
+            mass[r * NM + b] = make_double2(g[b0], g[b1] - g[b0]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PRO_THREADS)
+prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
+                unsigned int* __restrict__ ticket, EvalConsts ec) {
+    __shared__ double sm[9 * NM + 64];
+    __shared__ bool is_last;
+    __shared__ double th[NTHETA_MAX];
+    if (threadIdx.x < NTHETA_MAX) th[threadIdx.x] = (threadIdx.x < NTHETA || ec.use_wa) ? theta[threadIdx.x] : 0.0;
+    __syncthreads();
+    if (blockIdx.x < NM) pisn_row(th, blockIdx.x, aux, sm);
+    else cosmology_tables(th, ec.use_wa, aux, sm);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    build_records(aux, ec.use_wa, blob);
+    if (threadIdx.x == 0) {
+        build_scalars(th, aux, ec, blob + OFF_SCAL);
+        *ticket = 0u;
+    }
+}
+
+}  // namespace bump

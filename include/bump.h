@@ -1,0 +1,119 @@
+/*
+ * bump.h — C ABI of the B200-native BumpCosmology hyperlikelihood (libbump_b200.so).
+ *
+ * The reference has no FFI: its hot path is Python inlined in a numpyro model.  Each entry point below
+ * therefore names the reference *Python* interface it replaces (file:line under /root/reference/src/scripts).
+ * Plain pointers and sizes only; no torch / CUDA types.  All functions return 0 on success or a BUMP_E_*
+ * code, never throw, and leave a thread-local message readable through bump_last_error().
+ *
+ * theta layout (the derived parameters the reference's density objects receive, intensity_models.py:368-376):
+ *   [0] h  [1] Om  [2] w  [3] a  [4] b  [5] c  [6] mpisn  [7] mbhmax  [8] sigma  [9] fpl  [10] beta
+ *   [11] lam  [12] kappa  [13] zp          (BUMP_NTHETA = 14)
+ * and, only in the w0-wa extension mode, [14] wa (BASELINE.json config 5; no reference counterpart).
+ */
+#ifndef BUMP_H_
+#define BUMP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BUMP_NTHETA 14
+#define BUMP_NTHETA_MAX 15 /* with wa */
+
+/* Layout of the flat result vector written by bump_eval (doubles). */
+#define BUMP_OUT_LOGLIKE 0      /* sum_i [logsumexp_j w_ij - log nsamp]      'loglike' factor, intensity_models.py:382-383 */
+#define BUMP_OUT_LOG_MU_SEL 1   /* logsumexp_k w_k - log Ndraw               intensity_models.py:389 ('selfactor' = -nobs*this, :390) */
+#define BUMP_OUT_LOG_MU2 2      /* logsumexp_k 2 w_k - 2 log Ndraw           intensity_models.py:392 */
+#define BUMP_OUT_NEFF_SEL 3     /* exp(2 log_mu_sel - log_s2)                intensity_models.py:393-394 */
+#define BUMP_OUT_DLOGLIKE 4     /* d loglike / d theta[0..14]   (15 slots; slot 14 = wa, 0 unless wa mode) */
+#define BUMP_OUT_DLOG_MU 19     /* d log_mu_sel / d theta[0..14] */
+#define BUMP_OUT_NVALID_EVT 34  /* number of event samples with finite weight (diagnostic) */
+#define BUMP_OUT_NVALID_SEL 35  /* number of injections with finite weight (diagnostic) */
+#define BUMP_OUT_HEADER 40      /* neff[nobs_local] follows (intensity_models.py:401) */
+
+/* Per-rank partial for the multi-GPU exchange (doubles); see DESIGN.md "multi-GPU". */
+#define BUMP_PARTIAL_LEN 64
+
+#define BUMP_OK 0
+#define BUMP_E_INVALID 1   /* bad argument / call order */
+#define BUMP_E_CUDA 2      /* CUDA runtime error (message has the cudaError string) */
+#define BUMP_E_NOGPU 3     /* no CUDA device: there is NO CPU fallback */
+#define BUMP_E_NCCL 4      /* NCCL missing or failed */
+
+/* Evaluation flags (bump_ctx_create). */
+#define BUMP_FLAG_WA 1u        /* w0-wa (CPL) dark energy: theta has 15 entries */
+#define BUMP_FLAG_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
+
+typedef struct bump_ctx bump_ctx;
+
+/* Library / build information: returns e.g. "bump_b200 0.1 sm_100a". */
+const char* bump_version(void);
+const char* bump_last_error(void);
+int bump_device_count(void);
+
+/* One context = one GPU = one shard of the catalog.  Replaces the implicit XLA executable that numpyro builds
+ * around pop_cosmo_model (intensity_models.py:357; run_cosmo_fit.py:45-49). */
+int bump_ctx_create(bump_ctx** ctx, int device, uint32_t flags);
+void bump_ctx_destroy(bump_ctx* ctx);
+
+/* Upload this rank's events: four row-major [nobs, nsamp] float64 HOST arrays exactly as run_cosmo_fit.py:32-43
+ * builds them (m1s_det, qs, dls, pdraw).  theta-independent logs are precomputed on the device here
+ * (the reference recomputes log(pdraw) every trace, intensity_models.py:365).  nobs may be 0. */
+int bump_upload_events(bump_ctx* ctx, int64_t nobs, int64_t nsamp, const double* m1s_det, const double* qs,
+                       const double* dls, const double* pdraw);
+
+/* Upload this rank's found injections: four [nsel] float64 HOST arrays and the TOTAL number of draws
+ * (m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw of intensity_models.py:357; run_cosmo_fit.py:49). */
+int bump_upload_injections(bump_ctx* ctx, int64_t nsel, const double* m1s_det_sel, const double* qs_sel,
+                           const double* dls_sel, const double* pdraw_sel, double ndraw);
+
+/* Number of doubles bump_eval writes: BUMP_OUT_HEADER + nobs_local. */
+int64_t bump_out_len(const bump_ctx* ctx);
+
+/* One evaluation of the hot path (intensity_models.py:374-394,401 + its reverse pass): theta (HOST, 14 or 15
+ * doubles) -> out (HOST, bump_out_len doubles).  Synchronous: copies theta in, replays the kernel graph,
+ * copies the result out.  Non-finite or out-of-support theta yields NaN/-inf outputs, not an error
+ * (NUTS relies on that).  If a communicator is attached, the result is the merged all-rank value, identical
+ * bit for bit on every rank; neff[] stays local to the rank's events. */
+int bump_eval(bump_ctx* ctx, const double* theta, double* out);
+
+/* Same, fully asynchronous on a caller stream with DEVICE pointers (what an XLA FFI handler calls):
+ * no allocation, no host synchronisation.  stream is a cudaStream_t passed as void*. */
+int bump_eval_device(bump_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+
+/* Multi-GPU, host-driven exchange (torch.distributed or any allgather): produce this rank's partial
+ * (BUMP_PARTIAL_LEN doubles, HOST), then merge nranks partials in rank order into the final header
+ * (BUMP_OUT_HEADER doubles, HOST).  The merge is a pure function: every rank computes identical bits. */
+int bump_eval_partial(bump_ctx* ctx, const double* theta, double* partial, double* neff_local);
+int bump_merge_partials(const double* partials, int nranks, double* out_header);
+
+/* Multi-GPU, in-library exchange: one ncclAllGather of the partial + the same merge on the device, inside the
+ * evaluation graph.  id is the 128-byte ncclUniqueId produced by bump_nccl_unique_id on rank 0 and broadcast
+ * by the host (e.g. torch.distributed). */
+int bump_nccl_unique_id(void* id128);
+int bump_comm_attach(bump_ctx* ctx, const void* id128, int nranks, int rank);
+
+/* Introspection for unit-level parity tests of the prologue kernels (F1-F3 of SURVEY.md section 2.2):
+ * copies the theta-dependent tables of the last evaluation to the host.
+ *   which = 0: cosmology knots  [4][1024]: zinterp, dlinterp, ddlinterp, dvcinterp      (intensity_models.py:230-235)
+ *   which = 1: cosmology tangents [3 tables][2 or 3 params][1024]: d{dl,ddl,dvc}/d{Om,w[,wa]}
+ *   which = 2: PISN table [1 + 5][256]: log_dN_grid and its tangents d/d{a,b,mpisn,mbhmax,sigma} (:96-108)
+ *   which = 3: scalars [32]: log_pl_norm, log_norm, rate_log_norm, then their tangents */
+int bump_debug_tables(bump_ctx* ctx, int which, double* out, int64_t out_len);
+
+/* Timing helper for bench.py: run `iters` evaluations back to back on the context's stream with theta
+ * already on the device, bracketed by CUDA events ON THAT STREAM; returns total milliseconds and, if
+ * stream_ms is non-NULL, the milliseconds spent in the streaming kernel alone (events around each launch,
+ * graph replay disabled for that measurement). */
+int bump_time_evals(bump_ctx* ctx, const double* theta, int iters, float* total_ms, float* stream_ms);
+
+/* Number of kernel launches one bump_eval performs (for bench.py's gpu_launches). */
+int bump_launches_per_eval(const bump_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUMP_H_ */
