@@ -1,0 +1,221 @@
+// Epilogue: merge the per-tile partials of the streaming kernel into this rank's partial, and finalize the
+// (rank-merged) partials into the result header.
+//
+//   epilogue_kernel : per event, merge its tiles -> logsumexp (intensity_models.py:382), Neff (:401), normalised
+//                     gradient features; sum over events in a fixed order; merge the injection tiles (:389,392).
+//   finalize        : rank-ordered merge of PARTIAL_LEN-double partials, then the theta-only constants, the
+//                     selection statistics (:389-394) and the chain rule from features to d/dtheta.
+//                     `finalize_merge` is __host__ __device__: the same code backs bump_merge_partials (host) and
+//                     finalize_kernel (device), so every rank computes identical bits.
+#pragma once
+#include <math.h>
+
+#include "bump_layout.cuh"
+
+namespace bump {
+
+constexpr int EPI_THREADS = 512;
+
+// Gradient of (logsumexp + theta-only constant) from softmax-weighted features phi (already normalised and, for
+// events, summed over n events).  g[15] in theta order; sc = scalar block of the table blob.
+__host__ __device__ inline void grad_from_features(const double* phi, const double n, const double* sc, double* g) {
+    const double inv_h = sc[S_INV_H];
+    const double c = sc[S_C], M = sc[S_M], kappa = sc[S_KAPPA], zp = sc[S_ZP];
+    const double sq = phi[F_SQ];
+    const double geo = phi[F_GEO] * sc[S_INV_TOPM3];
+    const double* lpn = sc + S_LPN_D0;   // d log_pl_norm / d(a, b, mpisn, mbhmax, sigma)
+    const double* ln = sc + S_LN_D0;     // d log_norm / d(a, b, c, mpisn, mbhmax, sigma, fpl)
+    // cosmology: d_L, dd_L ~ 1/h and dV_C ~ 1/h^3 (intensity_models.py:231-239)
+    g[T_H] = (phi[F_CZ] - 2.0 * n) * inv_h;
+    g[T_OM] = phi[F_OM];
+    g[T_W] = phi[F_W];
+    // mass function (two evaluations per sample, each normalised by log_norm)
+    g[T_A] = phi[F_PA] + lpn[0] * sq + 2.0 * n * ln[0];
+    g[T_B] = phi[F_PB] + lpn[1] * sq + 2.0 * n * ln[1];
+    g[T_C] = -phi[F_C] + 2.0 * n * ln[2];
+    g[T_MPISN] = phi[F_PMPISN] + lpn[2] * sq + 2.0 * n * ln[3];
+    g[T_MBHMAX] = phi[F_PMBHMAX] - geo + sq * (c / M + lpn[3]) - phi[F_T] * sc[S_INV_DM] / M + 2.0 * n * ln[4];
+    g[T_SIGMA] = phi[F_PSIGMA] - 7.0 * geo + lpn[4] * sq + 2.0 * n * ln[5];
+    g[T_FPL] = sq / sc[S_FPL] + 2.0 * n * ln[6];
+    g[T_BETA] = phi[F_BETA] - n * LOG_MREF_PAIR;
+    // rate (intensity_models.py:167-173)
+    g[T_LAM] = phi[F_L];
+    g[T_KAPPA] = -(phi[F_SIGL] - sc[S_LOPZP] * phi[F_SIG]) + n * sc[S_LNV_KAPPA];
+    g[T_ZP] = phi[F_SIG] * kappa / (1.0 + zp) + n * sc[S_LNV_ZP];
+    g[T_WA] = (sc[S_USE_WA] != 0.0) ? phi[F_WA] : 0.0;
+}
+
+// partials: [nranks][PARTIAL_LEN] in rank order -> out[OUT_HEADER]
+__host__ __device__ inline void finalize_merge(const double* partials, const int nranks, double* out) {
+    const double* sc = partials + P_SCAL0;   // identical on every rank (same theta)
+    double llsum = 0.0, nobs = 0.0, nvalid_e = 0.0, nvalid_s = 0.0, nsel = 0.0, ndead = 0.0;
+    double phi[NFEAT];
+    for (int k = 0; k < NFEAT; ++k) phi[k] = 0.0;
+    double M = -INFINITY;
+    for (int r = 0; r < nranks; ++r) {
+        const double* p = partials + (size_t)r * PARTIAL_LEN;
+        llsum += p[P_LLSUM];
+        nobs += p[P_NOBS];
+        nvalid_e += p[P_NVALID_EVT];
+        nvalid_s += p[P_NVALID_SEL];
+        nsel += p[P_NSEL];
+        ndead += p[P_NDEAD_EVT];
+        for (int k = 0; k < NFEAT; ++k) phi[k] += p[P_FSUM0 + k];
+        M = fmax(M, p[P_SEL_M]);
+    }
+    double acc[NACC];
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (int r = 0; r < nranks; ++r) {
+        const double* p = partials + (size_t)r * PARTIAL_LEN;
+        if (p[P_SEL_M] == -INFINITY) continue;
+        const double s = exp(p[P_SEL_M] - M);
+        acc[0] += p[P_SEL_ACC0] * s;
+        acc[1] += p[P_SEL_ACC0 + 1] * (s * s);
+        for (int k = 2; k < NACC; ++k) acc[k] += p[P_SEL_ACC0 + k] * s;
+    }
+    for (int k = 0; k < OUT_HEADER; ++k) out[k] = 0.0;
+    const double cst = sc[S_CONST];
+    // events: 'loglike' factor (:382-383)
+    out[OUT_LOGLIKE] = (ndead > 0.0) ? -INFINITY : llsum + nobs * (cst - sc[S_LOG_NSAMP]);
+    grad_from_features(phi, nobs, sc, out + OUT_DLOGLIKE);
+    // injections (:389-394)
+    const double lnd = sc[S_LOG_NDRAW];
+    const double log_mu = M + log(acc[0]) + cst - lnd;
+    const double log_mu2 = 2.0 * M + log(acc[1]) + 2.0 * cst - 2.0 * lnd;
+    const double log_s2 = log_mu2 + log1p(-exp(2.0 * log_mu - lnd - log_mu2));
+    out[OUT_LOG_MU_SEL] = log_mu;
+    out[OUT_LOG_MU2] = log_mu2;
+    out[OUT_NEFF_SEL] = exp(2.0 * log_mu - log_s2);
+    double phis[NFEAT];
+    const double iS = 1.0 / acc[0];
+    for (int k = 0; k < NFEAT; ++k) phis[k] = acc[2 + k] * iS;
+    grad_from_features(phis, 1.0, sc, out + OUT_DLOG_MU);
+    out[OUT_NVALID_EVT] = nvalid_e;
+    out[OUT_NVALID_SEL] = nvalid_s;
+    out[OUT_NOBS] = nobs;
+    out[OUT_NSEL] = nsel;
+}
+
+__global__ void finalize_kernel(const double* __restrict__ partials, const int nranks, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) finalize_merge(partials, nranks, out);
+}
+
+// Merge two max-shifted accumulators (m, a[NACC]) <- (m, a) (+) (m2, b[NACC]).
+__device__ __forceinline__ void lse_merge(double& m, double* a, const double m2, const double* b) {
+    if (m2 == -INFINITY) return;
+    const double mx = fmax(m, m2);
+    const double s1 = (m == -INFINITY) ? 0.0 : exp(m - mx);
+    const double s2 = exp(m2 - mx);
+    a[0] = a[0] * s1 + b[0] * s2;
+    a[1] = a[1] * (s1 * s1) + b[1] * (s2 * s2);
+#pragma unroll
+    for (int k = 2; k < NACC; ++k) a[k] = a[k] * s1 + b[k] * s2;
+    m = mx;
+}
+
+// Deterministic block sum of NV values per thread (fixed shuffle tree, then fixed-order sum over warps).
+template <int NV>
+__device__ __forceinline__ void epi_block_sum(double (&v)[NV], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < EPI_THREADS / 32; ++w) s += red[w * NV + k];
+        v[k] = s;
+    }
+}
+
+// One block.  part: [ntiles][PART_STRIDE]; event e owns tiles [evt_tile_begin[e], evt_tile_begin[e+1]);
+// injection tiles are [n_evt_tiles, n_evt_tiles + n_sel_tiles).
+__global__ void __launch_bounds__(EPI_THREADS)
+epilogue_kernel(const double* __restrict__ part, const int* __restrict__ evt_tile_begin, const int nobs,
+                const int n_evt_tiles, const int n_sel_tiles, const double nsel, const double* __restrict__ blob,
+                double* __restrict__ neff_out, double* __restrict__ partial) {
+    __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
+    __shared__ double s_max;
+    const int tid = threadIdx.x;
+    // ---- events
+    double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
+#pragma unroll
+    for (int k = 0; k < NFEAT + 3; ++k) ev[k] = 0.0;
+    for (int e = tid; e < nobs; e += EPI_THREADS) {
+        double m = -INFINITY, a[NACC], nv = 0.0;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+        for (int t = evt_tile_begin[e]; t < evt_tile_begin[e + 1]; ++t) {
+            const double* p = part + (size_t)t * PART_STRIDE;
+            double b[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) b[k] = p[1 + k];
+            lse_merge(m, a, p[0], b);
+            nv += p[1 + NACC];
+        }
+        if (m == -INFINITY || !(a[0] > 0.0)) {   // no finite-weight sample: logsumexp = -inf (reference: same)
+            ev[2] += 1.0;
+            neff_out[e] = NAN;
+            continue;
+        }
+        const double iS = 1.0 / a[0];
+        ev[0] += m + log(a[0]);
+        ev[1] += nv;
+        neff_out[e] = a[0] * a[0] / a[1];   // exp(2 lse(w) - lse(2w)), :401
+#pragma unroll
+        for (int k = 0; k < NFEAT; ++k) ev[3 + k] += a[2 + k] * iS;
+    }
+    epi_block_sum<NFEAT + 3>(ev, red);
+    // ---- injections: global shift first, then plain sums
+    double mx = -INFINITY;
+    for (int t = tid; t < n_sel_tiles; t += EPI_THREADS) mx = fmax(mx, part[(size_t)(n_evt_tiles + t) * PART_STRIDE]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double m = red[0];
+        for (int w = 1; w < EPI_THREADS / 32; ++w) m = fmax(m, red[w]);
+        s_max = m;
+    }
+    __syncthreads();
+    mx = s_max;
+    double sv[NACC + 1];
+#pragma unroll
+    for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
+    for (int t = tid; t < n_sel_tiles; t += EPI_THREADS) {
+        const double* p = part + (size_t)(n_evt_tiles + t) * PART_STRIDE;
+        if (p[0] == -INFINITY) continue;
+        const double s = exp(p[0] - mx);
+        sv[0] += p[1] * s;
+        sv[1] += p[2] * (s * s);
+#pragma unroll
+        for (int k = 2; k < NACC; ++k) sv[k] += p[1 + k] * s;
+        sv[NACC] += p[1 + NACC];
+    }
+    epi_block_sum<NACC + 1>(sv, red);
+    if (tid == 0) {
+        for (int k = 0; k < P_SCAL0; ++k) partial[k] = 0.0;
+        partial[P_LLSUM] = ev[0];
+        partial[P_NOBS] = (double)nobs;
+        partial[P_NVALID_EVT] = ev[1];
+        partial[P_NDEAD_EVT] = ev[2];
+        for (int k = 0; k < NFEAT; ++k) partial[P_FSUM0 + k] = ev[3 + k];
+        partial[P_SEL_M] = mx;
+        for (int k = 0; k < NACC; ++k) partial[P_SEL_ACC0 + k] = sv[k];
+        partial[P_NVALID_SEL] = sv[NACC];
+        partial[P_NSEL] = nsel;
+    }
+    if (tid < NSCAL) partial[P_SCAL0 + tid] = blob[OFF_SCAL + tid];
+}
+
+}  // namespace bump

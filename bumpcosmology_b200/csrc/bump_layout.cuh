@@ -20,6 +20,7 @@ constexpr double C_H100_GPC = 2.99792; // :239
 constexpr double LOG_ZMAX1 = 4.6151205168412597;            // log(101)
 constexpr double ZSTEP = LOG_ZMAX1 / (NZ - 1);              // uniform step of the z grid in log(1+z)
 constexpr double LOG_MREF_PAIR = 4.0943445622221004;        // log(mref*(1+qref)) = log 60
+constexpr double LOG_MREF = 3.4011973816621555;             // log 30
 constexpr double LN2 = 0.69314718055994530942;
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;     // log(sqrt(2 pi))
 constexpr double FOUR_PI = 12.566370614359172954;
@@ -29,25 +30,36 @@ constexpr int NTHETA_MAX = 15;
 enum ThetaIdx { T_H = 0, T_OM, T_W, T_A, T_B, T_C, T_MPISN, T_MBHMAX, T_SIGMA, T_FPL, T_BETA, T_LAM, T_KAPPA,
                 T_ZP, T_WA };
 
-// ---- theta-dependent table blob: built by the prologue kernel in global memory, bulk-copied (TMA) to
-// shared memory by every CTA of the streaming kernel.  Offsets in doubles.
+// ---- theta-dependent table blob: built by the prologue kernel in global memory, bulk-copied (TMA) into the
+// shared memory of every CTA of the streaming kernel.  Offsets in doubles.
 constexpr int NSCAL = 64;
-constexpr int NCREC = 10;  // cosmology per-bin records {f0, f1-f0}
-constexpr int NMREC = 6;   // mass per-bin records
+constexpr int NCPAIR = 4;    // cosmology per-bin records {f_b, slope-like}
+constexpr int NCTAN = 9;     // cosmology tangent tables, one double per knot
+constexpr int NMREC = 6;     // mass per-bin records {g_b, g_{b+1}-g_b}
+// bucket table for the d_L search: key = top bits of the double (11 exponent bits + SRCH_MBITS mantissa bits)
+constexpr int SRCH_MBITS = 8;
+constexpr int SRCH_EXP_LO = -8 + 1023;    // biased exponent of 2^-8 Gpc
+constexpr int SRCH_OCTAVES = 21;          // 2^-8 .. 2^13 Gpc
+constexpr int SRCH_N = SRCH_OCTAVES << SRCH_MBITS;   // 5376 uint16 entries
+constexpr int SRCH_DOUBLES = SRCH_N / 4;
+
 constexpr int OFF_SCAL = 0;
-constexpr int OFF_COS = OFF_SCAL + NSCAL;           // double2 cos[NCREC][NZ]
-constexpr int OFF_DLK = OFF_COS + NCREC * NZ * 2;   // double dlk[NZ]     (search keys)
-constexpr int OFF_MASS = OFF_DLK + NZ;              // double2 mass[NMREC][NM]
+constexpr int OFF_COS = OFF_SCAL + NSCAL;               // double2 cos[NCPAIR][NZ]
+constexpr int OFF_CTAN = OFF_COS + NCPAIR * NZ * 2;     // double  ctan[NCTAN][NZ]
+constexpr int OFF_SRCH = OFF_CTAN + NCTAN * NZ;         // uint16  srch[SRCH_N]
+constexpr int OFF_MASS = OFF_SRCH + SRCH_DOUBLES;       // double2 mass[NMREC][NM]
 constexpr int BLOB_DOUBLES = OFF_MASS + NMREC * NM * 2;
 constexpr int BLOB_BYTES = BLOB_DOUBLES * 8;
 static_assert(BLOB_BYTES % 16 == 0, "bulk copies need 16-byte multiples");
+static_assert(SRCH_N % 4 == 0, "search table must fill whole doubles");
 
-// cosmology records, bin b = [knot b, knot b+1]
+// cosmology pair records, bin b = [knot b, knot b+1]
 enum CosRec { CR_DL = 0,   // {dl_b, 1/(dl_{b+1}-dl_b)}
               CR_DVC,      // {dvc_b, dvc_{b+1}-dvc_b}
-              CR_DDL,      // {ddl_b, ...}
-              CR_DL_OM, CR_DL_W, CR_DVC_OM, CR_DVC_W, CR_DDL_OM, CR_DDL_W,   // tangent tables, same form
+              CR_DDL,      // {ddl_b, ddl_{b+1}-ddl_b}
               CR_Z };      // {1/(1+z_b), log(1+z_b)}     theta-independent
+// cosmology tangent tables (knot values)
+enum CosTan { CT_DL_OM = 0, CT_DVC_OM, CT_DDL_OM, CT_DL_W, CT_DVC_W, CT_DDL_W, CT_DL_WA, CT_DVC_WA, CT_DDL_WA };
 // mass records, bin b of the mbh grid
 enum MassRec { MR_G = 0, MR_GA, MR_GB, MR_GMPISN, MR_GMBHMAX, MR_GSIGMA };
 
@@ -58,19 +70,21 @@ enum Scal {
     S_LPN_D0 = 20,   // d log_pl_norm / d(a, b, mpisn, mbhmax, sigma)          [5]
     S_LN_D0 = 25,    // d log_norm / d(a, b, c, mpisn, mbhmax, sigma, fpl)     [7]
     S_LNV_KAPPA = 32, S_LNV_ZP = 33,
-    S_LOG_NSAMP = 34, S_LOG_NDRAW = 35, S_NOBS_LOCAL = 36,
+    S_LOG_NSAMP = 34, S_LOG_NDRAW = 35, S_USE_WA = 36, S_DL_FIRST = 37,
+    S_EXP_LPN = 38,  // fpl * exp(PISN(mbhmax)) = exp(log_pl_norm)
+    S_ZEPS = 39,     // expm1(ZSTEP) = (z_{b+1}-z_b)/(1+z_b), the same for every bin of the log-uniform z grid
 };
 
-// ---- per-sample gradient features accumulated by the streaming kernel (see DESIGN.md for the algebra)
+// ---- per-sample gradient features accumulated by the streaming kernel (DESIGN.md has the algebra)
 enum Feat { F_CZ = 0, F_OM, F_W, F_SQ, F_C, F_PA, F_PB, F_PMPISN, F_PMBHMAX, F_PSIGMA, F_GEO, F_T, F_BETA, F_L,
-            F_SIG, F_SIGL, NFEAT };
-static_assert(NFEAT == 16, "16 features");
+            F_SIG, F_SIGL, F_WA, NFEAT };
+static_assert(NFEAT == 17, "17 features");
 constexpr int NACC = 2 + NFEAT;   // S, S2, features
-constexpr int PART_STRIDE = 20;   // per-tile partial: m, acc[18], nvalid
+constexpr int PART_STRIDE = 24;   // per-tile partial: [0] shift m, [1..19] acc, [20] nvalid
 
 // ---- tiles
 struct Tile {
-    int64_t off;   // first sample (index into the padded column arrays of its set)
+    int64_t off;   // first sample (index into the padded column arrays of its set); even
     int32_t count; // samples in the tile (even; may include sentinel padding)
     int32_t set;   // 0 = events, 1 = injections
 };
@@ -84,21 +98,23 @@ struct Columns {
 };
 
 // ---- per-rank partial (multi-GPU exchange); doubles
-constexpr int PARTIAL_SUMS = 64;
-constexpr int PARTIAL_LEN = 128;  // sums + copy of the scalars (for the host-side merge)
+constexpr int PARTIAL_LEN = 128;  // sums [0,64) + copy of the scalar block [64,128)
 enum PartialIdx {
-    P_LLSUM = 0,      // sum_e [log S_e + m_e]   (no constants)
+    P_LLSUM = 0,      // sum_e [log S_e + m_e]   (no theta-only constants)
     P_NOBS = 1,       // events in this shard
-    P_FSUM0 = 2,      // sum_e F_e[k]/S_e, k < 16
-    P_NVALID_EVT = 18,
-    P_SEL_M = 19,     // injection partial: running max, then acc[18]
-    P_SEL_ACC0 = 20,
-    P_NVALID_SEL = 38,
-    P_NSEL = 39,
+    P_FSUM0 = 2,      // sum_e F_e[k]/S_e, k < 17
+    P_NVALID_EVT = 19,
+    P_SEL_M = 20,     // injection partial: shift, then acc[19]
+    P_SEL_ACC0 = 21,
+    P_NVALID_SEL = 40,
+    P_NSEL = 41,
+    P_NDEAD_EVT = 42, // events without a single finite-weight sample (loglike = -inf)
+    P_SCAL0 = 64,
 };
 
 // output header (must match include/bump.h)
 constexpr int OUT_LOGLIKE = 0, OUT_LOG_MU_SEL = 1, OUT_LOG_MU2 = 2, OUT_NEFF_SEL = 3, OUT_DLOGLIKE = 4,
-              OUT_DLOG_MU = 19, OUT_NVALID_EVT = 34, OUT_NVALID_SEL = 35, OUT_HEADER = 40;
+              OUT_DLOG_MU = 19, OUT_NVALID_EVT = 34, OUT_NVALID_SEL = 35, OUT_NOBS = 36, OUT_NSEL = 37,
+              OUT_HEADER = 40;
 
 }  // namespace bump

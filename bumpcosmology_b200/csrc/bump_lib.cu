@@ -1,0 +1,564 @@
+// libbump_b200.so — C ABI (include/bump.h) over the sm_100a kernels.  CUDA runtime only; no torch, no CPU fallback.
+//
+// One evaluation = 4 launches replayed from a CUDA graph:
+//   prologue_kernel  (bump_tables.cuh)   theta -> tables + tangents + scalars           (F1-F3 of SURVEY.md 2.2)
+//   stream_kernel    (bump_stream.cuh)   one pass over the SoA columns -> per-tile sums (F4-F7 + reverse pass)
+//   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial
+//   [ncclAllGather of the 1 KiB partial when a communicator is attached]
+//   finalize_kernel  (bump_epilogue.cuh) rank-ordered merge, constants, chain rule -> result header
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bump.h"
+#include "bump_epilogue.cuh"
+#include "bump_layout.cuh"
+#include "bump_stream.cuh"
+#include "bump_tables.cuh"
+
+using namespace bump;
+
+static_assert(BUMP_NTHETA == NTHETA && BUMP_NTHETA_MAX == NTHETA_MAX, "theta layout");
+static_assert(BUMP_OUT_HEADER == OUT_HEADER && BUMP_OUT_DLOGLIKE == OUT_DLOGLIKE && BUMP_OUT_DLOG_MU == OUT_DLOG_MU,
+              "output layout");
+static_assert(BUMP_PARTIAL_LEN == PARTIAL_LEN, "partial layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(BUMP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                         std::to_string(__LINE__) + ")");                                 \
+    } while (0)
+
+// ---- NCCL through dlopen: the library loads (and the single-GPU path runs) without libnccl
+struct UniqueId {
+    char internal[128];
+};
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return BUMP_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(BUMP_E_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<int (*)(void**, int, UniqueId, int)>(dlsym(h, "ncclCommInitRank"));
+    a.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(
+        dlsym(h, "ncclAllGather"));
+    a.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy)
+        return fail(BUMP_E_NCCL, "libnccl is missing a required symbol");
+    g_nccl = a;
+    return BUMP_OK;
+}
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble in nccl.h
+
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0)                                                                               \
+            return fail(BUMP_E_NCCL, std::string(#call) + ": " +                                   \
+                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+    } while (0)
+
+// ---- upload-time kernel: raw (m1_det, q, d_L, pdraw) -> the 7 padded SoA columns (theta-independent logs hoisted;
+// the reference recomputes log(pdraw) on every trace, intensity_models.py:365)
+struct ColumnPtrs {
+    double* c[NCOL];
+};
+
+__global__ void prepare_columns_kernel(const double* __restrict__ m1d, const double* __restrict__ q,
+                                       const double* __restrict__ dl, const double* __restrict__ pd,
+                                       const int64_t nrows, const int64_t ncols, const int64_t stride,
+                                       ColumnPtrs out) {
+    const int64_t total = nrows * stride;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / stride, c = i - r * stride;
+        if (c < ncols) {
+            const int64_t s = r * ncols + c;
+            const double vm = m1d[s], vq = q[s];
+            out.c[C_DL][i] = dl[s];
+            out.c[C_M1D][i] = vm;
+            out.c[C_Q][i] = vq;
+            out.c[C_LM][i] = log(vm);
+            out.c[C_LQ][i] = log(vq);
+            out.c[C_L1Q][i] = log1p(vq);
+            out.c[C_LPD][i] = log(pd[s]);
+        } else {   // sentinel padding: source mass 1/(1+z) < mbh_min -> weight exactly zero (-inf log weight)
+            out.c[C_DL][i] = 1.0;
+            out.c[C_M1D][i] = 1.0;
+            out.c[C_Q][i] = 1.0;
+            out.c[C_LM][i] = 0.0;
+            out.c[C_LQ][i] = 0.0;
+            out.c[C_L1Q][i] = LN2;
+            out.c[C_LPD][i] = 0.0;
+        }
+    }
+}
+
+struct DataSet {
+    int64_t nrows = 0, ncols = 0, stride = 0;   // events: [nobs, nsamp]; injections: [1, nsel]
+    double* base = nullptr;                     // NCOL * nrows * stride doubles
+    double* col(int c) const { return base + (size_t)c * nrows * stride; }
+};
+
+}  // namespace
+
+struct bump_ctx {
+    int device = 0;
+    uint32_t flags = 0;
+    bool use_wa = false;
+    cudaStream_t stream = nullptr;
+    DataSet evt, sel;
+    double ndraw = 1.0;
+    // plan
+    bool plan_dirty = true;
+    int ntiles = 0, n_evt_tiles = 0, n_sel_tiles = 0, grid = 0, sm_count = 0;
+    Tile* d_tiles = nullptr;
+    int* d_evt_tile_begin = nullptr;
+    double* d_part = nullptr;
+    // workspaces
+    double *d_theta = nullptr, *d_aux = nullptr, *d_blob = nullptr, *d_partial = nullptr, *d_gather = nullptr,
+           *d_out = nullptr;
+    unsigned int* d_ticket = nullptr;
+    double *h_theta = nullptr, *h_out = nullptr;   // pinned
+    int64_t out_len = OUT_HEADER;
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // communicator
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int set_device(const bump_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return BUMP_OK;
+}
+
+void free_plan(bump_ctx* c) {
+    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    cudaFree(c->d_tiles), c->d_tiles = nullptr;
+    cudaFree(c->d_evt_tile_begin), c->d_evt_tile_begin = nullptr;
+    cudaFree(c->d_part), c->d_part = nullptr;
+    cudaFree(c->d_out), c->d_out = nullptr;
+    if (c->h_out) cudaFreeHost(c->h_out), c->h_out = nullptr;
+}
+
+int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const double* m1d, const double* q,
+               const double* dl, const double* pd) {
+    if (nrows < 0 || ncols < 0) return fail(BUMP_E_INVALID, "negative size");
+    if (nrows * ncols > 0 && (!m1d || !q || !dl || !pd)) return fail(BUMP_E_INVALID, "null data pointer");
+    if (int r = set_device(c)) return r;
+    cudaFree(ds.base);
+    ds = DataSet();
+    ds.nrows = nrows;
+    ds.ncols = ncols;
+    ds.stride = (ncols + 1) & ~int64_t(1);
+    c->plan_dirty = true;
+    const int64_t n = nrows * ncols, npad = nrows * ds.stride;
+    if (npad == 0) return BUMP_OK;
+    CK(cudaMalloc(&ds.base, sizeof(double) * NCOL * npad));
+    double* raw = nullptr;
+    CK(cudaMalloc(&raw, sizeof(double) * 4 * n));
+    const double* src[4] = {m1d, q, dl, pd};
+    for (int k = 0; k < 4; ++k)
+        CK(cudaMemcpyAsync(raw + (size_t)k * n, src[k], sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    ColumnPtrs cp;
+    for (int k = 0; k < NCOL; ++k) cp.c[k] = ds.col(k);
+    const int blocks = (int)std::min<int64_t>((npad + 255) / 256, 148 * 16);
+    prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, nrows, ncols,
+                                                          ds.stride, cp);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(raw));
+    return BUMP_OK;
+}
+
+// Split [0, n) (n even) into k chunks of even size, nearly equal.
+void split_even(int64_t base, int64_t n, int k, int set, std::vector<Tile>& tiles) {
+    const int64_t pairs = n / 2;
+    for (int i = 0; i < k; ++i) {
+        const int64_t lo = pairs * i / k, hi = pairs * (i + 1) / k;
+        if (hi > lo) tiles.push_back(Tile{base + 2 * lo, (int32_t)(2 * (hi - lo)), set});
+    }
+}
+
+int build_plan(bump_ctx* c) {
+    if (int r = set_device(c)) return r;
+    free_plan(c);
+    const int64_t ntot = c->evt.nrows * c->evt.stride + c->sel.nrows * c->sel.stride;
+    // tile size: aim at >= 4 tiles per SM, bounded so the per-tile block reduction stays a small fraction
+    int64_t target = (ntot / (4LL * c->sm_count) + 255) / 256 * 256;
+    target = std::min<int64_t>(std::max<int64_t>(target, 1024), 12288);
+    if (const char* e = getenv("BUMP_TILE")) target = std::max<int64_t>(256, atoll(e) / 2 * 2);
+    std::vector<Tile> tiles;
+    std::vector<int> begin(c->evt.nrows + 1, 0);
+    for (int64_t e = 0; e < c->evt.nrows; ++e) {
+        begin[e] = (int)tiles.size();
+        const int k = (int)std::max<int64_t>(1, (c->evt.stride + target - 1) / target);
+        split_even(e * c->evt.stride, c->evt.stride, k, 0, tiles);
+    }
+    begin[c->evt.nrows] = (int)tiles.size();
+    c->n_evt_tiles = (int)tiles.size();
+    if (c->sel.nrows * c->sel.stride > 0) {
+        const int k = (int)std::max<int64_t>(1, (c->sel.stride + target - 1) / target);
+        split_even(0, c->sel.stride, k, 1, tiles);
+    }
+    c->ntiles = (int)tiles.size();
+    c->n_sel_tiles = c->ntiles - c->n_evt_tiles;
+    c->grid = std::max(1, std::min(c->ntiles, c->sm_count));
+    c->out_len = OUT_HEADER + c->evt.nrows;
+    CK(cudaMalloc(&c->d_tiles, sizeof(Tile) * std::max<size_t>(1, tiles.size())));
+    CK(cudaMalloc(&c->d_evt_tile_begin, sizeof(int) * begin.size()));
+    CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max<size_t>(1, tiles.size())));
+    CK(cudaMalloc(&c->d_out, sizeof(double) * c->out_len));
+    CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
+    if (!tiles.empty())
+        CK(cudaMemcpy(c->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_evt_tile_begin, begin.data(), sizeof(int) * begin.size(), cudaMemcpyHostToDevice));
+    c->plan_dirty = false;
+    return BUMP_OK;
+}
+
+Columns columns_of(const bump_ctx* c) {
+    Columns cols;
+    for (int k = 0; k < NCOL; ++k) {
+        cols.evt[k] = c->evt.base ? c->evt.col(k) : nullptr;
+        cols.sel[k] = c->sel.base ? c->sel.col(k) : nullptr;
+    }
+    return cols;
+}
+
+EvalConsts consts_of(const bump_ctx* c) {
+    EvalConsts ec;
+    ec.log_nsamp = log((double)std::max<int64_t>(c->evt.ncols, 1));
+    ec.log_ndraw = log(c->ndraw);
+    ec.use_wa = c->use_wa ? 1 : 0;
+    return ec;
+}
+
+// The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
+int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
+                   cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr) {
+    prologue_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket, consts_of(c));
+    if (k0) cudaEventRecord(k0, s);
+    if (c->ntiles > 0) {
+        if (c->use_wa)
+            stream_kernel<true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->d_tiles, c->ntiles,
+                                                                                   c->d_blob, c->d_part);
+        else
+            stream_kernel<false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->d_tiles,
+                                                                                    c->ntiles, c->d_blob, c->d_part);
+    }
+    if (k1) cudaEventRecord(k1, s);
+    epilogue_kernel<<<1, EPI_THREADS, 0, s>>>(c->d_part, c->d_evt_tile_begin, (int)c->evt.nrows, c->n_evt_tiles,
+                                              c->n_sel_tiles, (double)c->sel.ncols, c->d_blob, neff_dev, partial_dev);
+    CK(cudaGetLastError());
+    return BUMP_OK;
+}
+
+int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStream_t s, cudaEvent_t k0 = nullptr,
+                cudaEvent_t k1 = nullptr) {
+    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1)) return r;
+    const double* merged = c->d_partial;
+    if (c->comm) {
+        NCK(g_nccl.AllGather(c->d_partial, c->d_gather, PARTIAL_LEN, NCCL_FLOAT64, c->comm, s));
+        merged = c->d_gather;
+    }
+    finalize_kernel<<<1, 32, 0, s>>>(merged, c->nranks, out_dev);
+    CK(cudaGetLastError());
+    return BUMP_OK;
+}
+
+int ensure_ready(bump_ctx* c) {
+    if (!c) return fail(BUMP_E_INVALID, "null context");
+    if (int r = set_device(c)) return r;
+    if (c->plan_dirty)
+        if (int r = build_plan(c)) return r;
+    return BUMP_OK;
+}
+
+int ensure_graph(bump_ctx* c) {
+    if (c->graph || (c->flags & BUMP_FLAG_NO_GRAPH)) return BUMP_OK;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int r = launch_eval(c, c->d_theta, c->d_out, c->stream);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (r) {
+        if (g) cudaGraphDestroy(g);
+        return r;
+    }
+    CK(e);
+    CK(cudaGraphInstantiate(&c->graph, g, 0));
+    CK(cudaGraphDestroy(g));
+    return BUMP_OK;
+}
+
+int run_once(bump_ctx* c) {   // d_theta -> d_out on the context stream
+    if (c->flags & BUMP_FLAG_NO_GRAPH) return launch_eval(c, c->d_theta, c->d_out, c->stream);
+    if (int r = ensure_graph(c)) return r;
+    CK(cudaGraphLaunch(c->graph, c->stream));
+    return BUMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bump_version(void) { return "bump_b200 0.1 sm_100a"; }
+const char* bump_last_error(void) { return g_err.c_str(); }
+
+int bump_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
+    if (!out) return fail(BUMP_E_INVALID, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(BUMP_E_NOGPU, "no CUDA device visible: bump_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(BUMP_E_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BUMP_E_NOGPU, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                      "; this library is built for sm_100a only");
+    bump_ctx* c = new bump_ctx();
+    c->device = device;
+    c->flags = flags;
+    c->use_wa = (flags & BUMP_FLAG_WA) != 0;
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
+    CK(cudaMemset(c->d_theta, 0, sizeof(double) * NTHETA_MAX));
+    CK(cudaMalloc(&c->d_aux, sizeof(double) * AUX_DOUBLES));
+    CK(cudaMalloc(&c->d_blob, BLOB_BYTES));
+    CK(cudaMemset(c->d_blob, 0, BLOB_BYTES));
+    CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
+    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
+    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaFuncSetAttribute(stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    *out = c;
+    return BUMP_OK;
+}
+
+void bump_ctx_destroy(bump_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_plan(c);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->evt.base);
+    cudaFree(c->sel.base);
+    cudaFree(c->d_theta);
+    cudaFree(c->d_aux);
+    cudaFree(c->d_blob);
+    cudaFree(c->d_partial);
+    cudaFree(c->d_gather);
+    cudaFree(c->d_ticket);
+    if (c->h_theta) cudaFreeHost(c->h_theta);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bump_upload_events(bump_ctx* c, int64_t nobs, int64_t nsamp, const double* m1s_det, const double* qs,
+                       const double* dls, const double* pdraw) {
+    if (!c) return fail(BUMP_E_INVALID, "null context");
+    return upload_set(c, c->evt, nobs, nsamp, m1s_det, qs, dls, pdraw);
+}
+
+int bump_upload_injections(bump_ctx* c, int64_t nsel, const double* m1s_det_sel, const double* qs_sel,
+                           const double* dls_sel, const double* pdraw_sel, double ndraw) {
+    if (!c) return fail(BUMP_E_INVALID, "null context");
+    if (!(ndraw > 0.0)) return fail(BUMP_E_INVALID, "ndraw must be positive");
+    c->ndraw = ndraw;
+    return upload_set(c, c->sel, nsel > 0 ? 1 : 0, nsel, m1s_det_sel, qs_sel, dls_sel, pdraw_sel);
+}
+
+int64_t bump_out_len(const bump_ctx* c) { return c ? OUT_HEADER + c->evt.nrows : 0; }
+
+int bump_eval(bump_ctx* c, const double* theta, double* out) {
+    if (!theta || !out) return fail(BUMP_E_INVALID, "null theta/out");
+    if (int r = ensure_ready(c)) return r;
+    const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
+    memcpy(c->h_theta, theta, sizeof(double) * nth);
+    CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+    if (int r = run_once(c)) return r;
+    CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * c->out_len, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_out, sizeof(double) * c->out_len);
+    return BUMP_OK;
+}
+
+int bump_eval_device(bump_ctx* c, const double* theta_dev, double* out_dev, void* stream) {
+    if (!theta_dev || !out_dev) return fail(BUMP_E_INVALID, "null theta/out");
+    if (int r = ensure_ready(c)) return r;
+    return launch_eval(c, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int bump_eval_partial_device(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev,
+                             void* stream) {
+    if (!theta_dev || !partial_dev) return fail(BUMP_E_INVALID, "null theta/partial");
+    if (int r = ensure_ready(c)) return r;
+    return launch_partial(c, theta_dev, partial_dev, neff_dev ? neff_dev : c->d_out + OUT_HEADER,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int bump_finalize_device(bump_ctx* c, const double* partials_dev, int nranks, double* out_header_dev, void* stream) {
+    if (!c || !partials_dev || !out_header_dev || nranks < 1) return fail(BUMP_E_INVALID, "bad finalize arguments");
+    if (int r = set_device(c)) return r;
+    finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials_dev, nranks, out_header_dev);
+    CK(cudaGetLastError());
+    return BUMP_OK;
+}
+
+int bump_eval_partial(bump_ctx* c, const double* theta, double* partial, double* neff_local) {
+    if (!theta || !partial) return fail(BUMP_E_INVALID, "null theta/partial");
+    if (int r = ensure_ready(c)) return r;
+    const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
+    memcpy(c->h_theta, theta, sizeof(double) * nth);
+    CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+    if (int r = launch_partial(c, c->d_theta, c->d_partial, c->d_out + OUT_HEADER, c->stream)) return r;
+    CK(cudaMemcpyAsync(partial, c->d_partial, sizeof(double) * PARTIAL_LEN, cudaMemcpyDeviceToHost, c->stream));
+    if (neff_local && c->evt.nrows > 0)
+        CK(cudaMemcpyAsync(neff_local, c->d_out + OUT_HEADER, sizeof(double) * c->evt.nrows, cudaMemcpyDeviceToHost,
+                           c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BUMP_OK;
+}
+
+int bump_merge_partials(const double* partials, int nranks, double* out_header) {
+    if (!partials || !out_header || nranks < 1) return fail(BUMP_E_INVALID, "bad merge arguments");
+    finalize_merge(partials, nranks, out_header);
+    return BUMP_OK;
+}
+
+int bump_nccl_unique_id(void* id128) {
+    if (!id128) return fail(BUMP_E_INVALID, "null id");
+    if (int r = load_nccl()) return r;
+    NCK(g_nccl.GetUniqueId(id128));
+    return BUMP_OK;
+}
+
+int bump_comm_attach(bump_ctx* c, const void* id128, int nranks, int rank) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(BUMP_E_INVALID, "bad comm arguments");
+    if (int r = load_nccl()) return r;
+    if (int r = set_device(c)) return r;
+    UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    cudaFree(c->d_gather);
+    CK(cudaMalloc(&c->d_gather, sizeof(double) * PARTIAL_LEN * nranks));
+    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    return BUMP_OK;
+}
+
+int bump_debug_tables(bump_ctx* c, int which, double* out, int64_t out_len) {
+    if (!c || !out) return fail(BUMP_E_INVALID, "null argument");
+    if (int r = set_device(c)) return r;
+    const double* src = nullptr;
+    int64_t n = 0;
+    switch (which) {
+        case 0: src = c->d_aux + AUX_ZG, n = 4 * NZ; break;
+        case 1: src = c->d_aux + AUX_TAN, n = 9 * NZ; break;
+        case 2: src = c->d_aux + AUX_G, n = 6 * NM; break;
+        case 3: src = c->d_blob + OFF_SCAL, n = NSCAL; break;
+        default: return fail(BUMP_E_INVALID, "unknown table id");
+    }
+    if (out_len < n) return fail(BUMP_E_INVALID, "output buffer too small");
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return BUMP_OK;
+}
+
+int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms, float* stream_ms) {
+    if (!theta || iters < 1 || !total_ms) return fail(BUMP_E_INVALID, "bad timing arguments");
+    if (int r = ensure_ready(c)) return r;
+    const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
+    memcpy(c->h_theta, theta, sizeof(double) * nth);
+    CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+    if (int r = ensure_graph(c)) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < iters; ++i)
+        if (int r = run_once(c)) return r;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(total_ms, c->ev0, c->ev1));
+    if (stream_ms) {   // the streaming kernel alone: events around each direct launch on the same stream
+        float acc = 0.f;
+        for (int i = 0; i < iters; ++i) {
+            if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, c->ev0, c->ev1)) return r;
+            CK(cudaEventSynchronize(c->ev1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            acc += ms;
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        *stream_ms = acc;
+    }
+    return BUMP_OK;
+}
+
+int bump_launches_per_eval(const bump_ctx* c) { return c ? 4 : 0; }
+
+int bump_plan_info(bump_ctx* c, int64_t* info8) {
+    if (!info8) return fail(BUMP_E_INVALID, "null info");
+    if (int r = ensure_ready(c)) return r;
+    info8[0] = c->ntiles;
+    info8[1] = c->n_evt_tiles;
+    info8[2] = c->n_sel_tiles;
+    info8[3] = c->grid;
+    info8[4] = STREAM_THREADS;
+    info8[5] = STREAM_SMEM_BYTES;
+    info8[6] = c->evt.nrows * c->evt.stride + c->sel.nrows * c->sel.stride;
+    info8[7] = c->sm_count;
+    return BUMP_OK;
+}
+
+}  // extern "C"

@@ -20,9 +20,6 @@ constexpr int STREAM_THREADS = BUMP_STREAM_THREADS;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/ + STREAM_WARPS * (NACC + 2) * 8;
 constexpr double RESCALE_GAP = 60.0;   // rescale the running shift when a weight exceeds it by e^60
-constexpr double ZEPS = 0.0045216907256407;  // placeholder, overwritten by expm1(ZSTEP) at compile time below
-
-__device__ __forceinline__ double zeps() { return 4.5216907256407297e-03; }  // expm1(log(101)/1023)
 
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,22 +104,22 @@ __device__ __forceinline__ double mass_term(const double m, const double lm, con
     return A0;
 }
 
+template <bool WA>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
                                             const double* __restrict__ s_blob, SampleOut& o) {
     const double* __restrict__ sc = s_blob + OFF_SCAL;
     const double2* __restrict__ cos = reinterpret_cast<const double2*>(s_blob + OFF_COS);
-    const double* __restrict__ dlk = s_blob + OFF_DLK;
+    const double* __restrict__ ctan = s_blob + OFF_CTAN;
+    const unsigned short* __restrict__ srch = reinterpret_cast<const unsigned short*>(s_blob + OFF_SRCH);
     const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
 
-    // ---- z_of_dL: searchsorted(side='right') over the d_L knots, clipped to [1, n-1]   (:272-273)
-    const long long xi = __double_as_longlong(x);   // positive doubles order like their bit patterns
-    int pos = 0;
-#pragma unroll
-    for (int step = NZ / 2; step >= 1; step >>= 1) {
-        if (__double_as_longlong(dlk[pos + step - 1]) <= xi) pos += step;
-    }
-    const int b = max(pos, 1) - 1;
+    // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
+    // bucket table keyed by the top bits of x gives a lower bound of the bin; walk up to the exact one.
+    int j = (__double2hiint(x) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
+    j = min(max(j, 0), SRCH_N - 1);
+    int b = srch[j];
+    while (b < NZ - 2 && x >= cos[CR_DL * NZ + b + 1].x) ++b;
     const bool beyond = x > sc[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     const double2 rdl = cos[CR_DL * NZ + b];
     double t = (x - rdl.x) * rdl.y;
@@ -130,11 +127,12 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     t = beyond ? 1.0 : t;
     // ---- position inside the z bin: 1+z = (1+z_b)(1 + t eps)
     const double2 rz = cos[CR_Z * NZ + b];
-    const double te = t * zeps();
+    const double zeps = sc[S_ZEPS];
+    const double te = t * zeps;
     const double u1 = frcp1p_small(te);
     const double ropz = rz.x * u1;                  // 1/(1+z)
     const double L = rz.y + flog1p_small(te);       // log1p(z)
-    const double lt = zeps() * u1;                  // dL/dt
+    const double lt = zeps * u1;                    // dL/dt
     // ---- source-frame masses (:379, :207)
     double m1 = m1d * ropz;
     double m2 = q * m1;
@@ -142,7 +140,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     double lm2 = lm1 + lq;
     bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);   // :149
     if (!valid) {   // keep every intermediate finite; the sample gets zero weight below
-        m1 = MREF; m2 = MREF; lm1 = 3.4011973816621555; lm2 = lm1;
+        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
     }
     // ---- dVC/dz and d(dL)/dz lerps at z (:264-268), same bin, same t
     const double2 rvc = cos[CR_DVC * NZ + b];
@@ -166,16 +164,19 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double A2 = mass_term(m2, lm2, sc, mass, o.f, mdA2);
     const double pair = lm1 + l1q;                  // log(m1+m2); the -log(60) is in the constant
     double w = A1 + A2 + fma(beta, pair, lm1) + V0 - 2.0 * L + ljac - lpd;   // :210, :381
-    // ---- d w / d t at fixed tables, then the three cosmological tangents
+    // ---- d w / d t at fixed tables, then the cosmological tangents
     const double Wt = lt * (lam - kappa * sig - 3.0 - beta - mdA1 - mdA2) + rvc.y * idvc - rdd.y * iddl;
-    const double Wx = Wt * idl;                     // times -(d dl-table/d theta)(t) gives d z-position terms
+    const double Wx = Wt * idl;                     // -Wx * (d dl-table / d theta)(t) = (dw/dt)(dt/dtheta)
     o.f[F_CZ] = Wx * x;
-    {
-        const double2 a0 = cos[CR_DL_OM * NZ + b], a1 = cos[CR_DVC_OM * NZ + b], a2 = cos[CR_DDL_OM * NZ + b];
-        o.f[F_OM] = fma(-Wx, fma(t, a0.y, a0.x), fma(t, a1.y, a1.x) * idvc - fma(t, a2.y, a2.x) * iddl);
-        const double2 b0 = cos[CR_DL_W * NZ + b], b1 = cos[CR_DVC_W * NZ + b], b2 = cos[CR_DDL_W * NZ + b];
-        o.f[F_W] = fma(-Wx, fma(t, b0.y, b0.x), fma(t, b1.y, b1.x) * idvc - fma(t, b2.y, b2.x) * iddl);
-    }
+    auto tangent = [&](const int tdl, const int tdvc, const int tddl) -> double {
+        const double a0 = ctan[tdl * NZ + b], a1 = ctan[tdl * NZ + b + 1];
+        const double v0 = ctan[tdvc * NZ + b], v1 = ctan[tdvc * NZ + b + 1];
+        const double d0 = ctan[tddl * NZ + b], d1 = ctan[tddl * NZ + b + 1];
+        return fma(-Wx, fma(t, a1 - a0, a0), fma(t, v1 - v0, v0) * idvc - fma(t, d1 - d0, d0) * iddl);
+    };
+    o.f[F_OM] = tangent(CT_DL_OM, CT_DVC_OM, CT_DDL_OM);
+    o.f[F_W] = tangent(CT_DL_W, CT_DVC_W, CT_DDL_W);
+    if constexpr (WA) o.f[F_WA] = tangent(CT_DL_WA, CT_DVC_WA, CT_DDL_WA);
     o.f[F_BETA] = pair;
     o.f[F_L] = L;
     o.f[F_SIG] = sig;
@@ -251,11 +252,12 @@ __device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* _
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < STREAM_WARPS; ++w) s += r2[w * (NACC + 1) + threadIdx.x];
-        out[1 + threadIdx.x] = s;
+        out[1 + threadIdx.x] = s;   // [1..NACC] sums, [NACC+1] nvalid
     }
     if (threadIdx.x == 0) out[0] = mx;
 }
 
+template <bool WA>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
 stream_kernel(const Columns cols, const Tile* __restrict__ tiles, const int ntiles,
               const double* __restrict__ g_blob, double* __restrict__ part) {
@@ -283,9 +285,9 @@ stream_kernel(const Columns cols, const Tile* __restrict__ tiles, const int ntil
             const double2 dl = __ldg(c_dl + p), m1 = __ldg(c_m1 + p), q = __ldg(c_q + p), lm = __ldg(c_lm + p),
                           lq = __ldg(c_lq + p), l1q = __ldg(c_l1q + p), lpd = __ldg(c_lpd + p);
             SampleOut o;
-            eval_sample(dl.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, o);
+            eval_sample<WA>(dl.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, o);
             acc_add(A, o);
-            eval_sample(dl.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, o);
+            eval_sample<WA>(dl.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, o);
             acc_add(A, o);
         }
         tile_reduce(A, red, part + (size_t)tile * PART_STRIDE);

@@ -31,7 +31,6 @@ struct CgView {
 struct EvalConsts {   // theta-independent numbers the prologue copies into the scalar block
     double log_nsamp;
     double log_ndraw;
-    double nobs_local;
     int use_wa;
 };
 
@@ -273,33 +272,32 @@ __device__ void build_scalars(const double* th, const double* aux_, const EvalCo
     scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
     scal[S_LOG_NSAMP] = ec.log_nsamp;
     scal[S_LOG_NDRAW] = ec.log_ndraw;
-    scal[S_NOBS_LOCAL] = ec.nobs_local;
+    scal[S_USE_WA] = (double)ec.use_wa;
+    scal[S_DL_FIRST] = aux[AUX_DL + 0];
+    scal[S_EXP_LPN] = exp(lpn.v);
+    scal[S_ZEPS] = expm1(ZSTEP);
 }
 
 __device__ void build_records(const double* aux_, int use_wa, double* blob) {
     const CgView aux{aux_};
     double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
+    double* ctan = blob + OFF_CTAN;
     double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
-    double* dlk = blob + OFF_DLK;
+    unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
+    const CgView dl = aux + AUX_DL;
     for (int b = threadIdx.x; b < NZ; b += blockDim.x) {
-        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // bin NZ-1 is padding (copy of the last bin)
-        const CgView dl = aux + AUX_DL;
+        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
         cos[CR_DL * NZ + b] = make_double2(dl[b0], 1.0 / (dl[b1] - dl[b0]));
         const CgView dvc = aux + AUX_DVC;
         cos[CR_DVC * NZ + b] = make_double2(dvc[b0], dvc[b1] - dvc[b0]);
         const CgView ddl = aux + AUX_DDL;
         cos[CR_DDL * NZ + b] = make_double2(ddl[b0], ddl[b1] - ddl[b0]);
-        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa]
-        const int recs[6] = {CR_DL_OM, CR_DL_W, CR_DDL_OM, CR_DDL_W, CR_DVC_OM, CR_DVC_W};
-        const int srcs[6] = {0 * 3 + 0, 0 * 3 + 1, 1 * 3 + 0, 1 * 3 + 1, 2 * 3 + 0, 2 * 3 + 1};
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const CgView t = aux + (AUX_TAN + srcs[r] * NZ);
-            cos[recs[r] * NZ + b] = make_double2(t[b0], t[b1] - t[b0]);
-        }
-        const double lz = (b0 >= NZ - 1) ? LOG_ZMAX1 : b0 * ZSTEP;
+        const double lz = b0 * ZSTEP;
         cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), lz);
-        dlk[b] = dl[b];
+        // tangent tables (knot values): aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan
+        const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
+#pragma unroll
+        for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
     }
     for (int b = threadIdx.x; b < NM; b += blockDim.x) {
         const int b0 = min(b, NM - 2), b1 = b0 + 1;
@@ -308,6 +306,18 @@ __device__ void build_records(const double* aux_, int use_wa, double* blob) {
             const CgView g = aux + (AUX_G + r * NM);
             mass[r * NM + b] = make_double2(g[b0], g[b1] - g[b0]);
         }
+    }
+    // bucket table for the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j
+    for (int j = threadIdx.x; j < SRCH_N; j += blockDim.x) {
+        const int key = j + (SRCH_EXP_LO << SRCH_MBITS);
+        const double x0 = __hiloint2double(key << (20 - SRCH_MBITS), 0);   // smallest double of the bucket
+        int pos = 0;                                                        // #{k < NZ-1 : dl_k <= x0}
+#pragma unroll 1
+        for (int step = NZ / 2; step >= 1; step >>= 1) {
+            if (dl[pos + step - 1] <= x0) pos += step;
+        }
+        const int b = min(max(pos, 1) - 1, NZ - 2);
+        srch[j] = (unsigned short)(j == 0 ? 0 : b);
     }
 }
 

@@ -32,10 +32,12 @@ extern "C" {
 #define BUMP_OUT_DLOG_MU 19     /* d log_mu_sel / d theta[0..14] */
 #define BUMP_OUT_NVALID_EVT 34  /* number of event samples with finite weight (diagnostic) */
 #define BUMP_OUT_NVALID_SEL 35  /* number of injections with finite weight (diagnostic) */
+#define BUMP_OUT_NOBS 36        /* total number of events over all ranks */
+#define BUMP_OUT_NSEL 37        /* total number of found injections over all ranks */
 #define BUMP_OUT_HEADER 40      /* neff[nobs_local] follows (intensity_models.py:401) */
 
 /* Per-rank partial for the multi-GPU exchange (doubles); see DESIGN.md "multi-GPU". */
-#define BUMP_PARTIAL_LEN 64
+#define BUMP_PARTIAL_LEN 128
 
 #define BUMP_OK 0
 #define BUMP_E_INVALID 1   /* bad argument / call order */
@@ -90,6 +92,15 @@ int bump_eval_device(bump_ctx* ctx, const double* theta_dev, double* out_dev, vo
 int bump_eval_partial(bump_ctx* ctx, const double* theta, double* partial, double* neff_local);
 int bump_merge_partials(const double* partials, int nranks, double* out_header);
 
+/* Multi-GPU, caller-driven exchange ON THE DEVICE (torch.distributed all_gather_into_tensor between the two
+ * calls, everything on one caller stream, no host synchronisation): this rank's partial (BUMP_PARTIAL_LEN
+ * doubles, DEVICE) and neff (nobs_local doubles, DEVICE; may be NULL), then the rank-ordered merge of the
+ * gathered [nranks][BUMP_PARTIAL_LEN] partials into the result header (BUMP_OUT_HEADER doubles, DEVICE). */
+int bump_eval_partial_device(bump_ctx* ctx, const double* theta_dev, double* partial_dev, double* neff_dev,
+                             void* stream);
+int bump_finalize_device(bump_ctx* ctx, const double* partials_dev, int nranks, double* out_header_dev,
+                         void* stream);
+
 /* Multi-GPU, in-library exchange: one ncclAllGather of the partial + the same merge on the device, inside the
  * evaluation graph.  id is the 128-byte ncclUniqueId produced by bump_nccl_unique_id on rank 0 and broadcast
  * by the host (e.g. torch.distributed). */
@@ -112,6 +123,10 @@ int bump_time_evals(bump_ctx* ctx, const double* theta, int iters, float* total_
 
 /* Number of kernel launches one bump_eval performs (for bench.py's gpu_launches). */
 int bump_launches_per_eval(const bump_ctx* ctx);
+
+/* Execution plan of the streaming kernel: info8 = {tiles, event tiles, injection tiles, grid (CTAs), threads
+ * per CTA, dynamic shared memory bytes, padded samples resident on this rank, SM count}. */
+int bump_plan_info(bump_ctx* ctx, int64_t* info8);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,172 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors minted from the unmodified reference
+and with the fp64 oracle.  Tolerance: 1e-10 relative (north star, fp64), with an absolute floor of 1e-10 times
+the gradient scale for near-zero components."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"pop_cosmo_{name}.npz"))
+
+
+def _data(g):
+    return (g["m1s_det"], g["qs"], g["dls"], g["pdraw"], g["m1s_det_sel"], g["qs_sel"], g["dls_sel"],
+            g["pdraw_sel"], float(g["Ndraw"]))
+
+
+def _close(a, b, rtol=RTOL, floor=1.0):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), floor)))
+
+
+def _sites_grad(g, th):
+    from oracle import bump_oracle as bo
+    return bo.grad_sites_from_theta(g, th)
+
+
+@pytest.fixture(scope="module")
+def hl():
+    from bumpcosmology_b200.likelihood import Hyperlikelihood
+    return Hyperlikelihood
+
+
+@pytest.mark.parametrize("name", ("tiny", "small"))
+def test_cuda_matches_reference_goldens(golden_dir, hl, name):
+    g = _load(golden_dir, name)
+    like = hl(*_data(g))
+    for k, th in enumerate(g["thetas"]):
+        r = like(th)
+        assert _close(r.loglike, g["ref_loglike"][k]), (k, r.loglike, g["ref_loglike"][k])
+        assert _close(r.log_mu_sel, g["ref_log_mu_sel"][k])
+        assert _close(r.selfactor, g["ref_selfactor"][k])
+        assert _close(r.neff_sel, g["ref_neff_sel"][k])
+        assert _close(r.neff, g["ref_neff"][k])
+        scale = max(1.0, float(np.max(np.abs(g["ref_dloglike_dsite"][k]))))
+        assert _close(_sites_grad(r.dloglike[:14], th), g["ref_dloglike_dsite"][k], floor=scale), k
+        assert _close(_sites_grad(r.dlog_mu_sel[:14], th), g["ref_dlog_mu_sel_dsite"][k]), k
+    like.close()
+
+
+@pytest.mark.parametrize("name", ("tiny", "small"))
+def test_cuda_tables_match_reference(golden_dir, hl, name):
+    g = _load(golden_dir, name)
+    like = hl(*_data(g))
+    for k, th in enumerate(g["thetas"]):
+        like(th)
+        t = like.tables()
+        for key in ("zinterp", "dlinterp", "ddlinterp", "dvcinterp", "log_dN_grid"):
+            assert _close(t[key], g["tab_" + key][k], rtol=1e-12, floor=1e-3), (k, key)
+    like.close()
+
+
+def test_cuda_table_tangents_match_oracle_autograd(golden_dir, hl):
+    from oracle import bump_oracle as bo
+    g = _load(golden_dir, "tiny")
+    like = hl(*_data(g))
+    for th in g["thetas"][:3]:
+        like(th)
+        t = like.tables()
+        jac = bo.table_jacobians(th)
+        sc = t["scalars"]
+        for name, key in (("d_dl", "dlinterp"), ("d_ddl", "ddlinterp"), ("d_dvc", "dvcinterp")):
+            for c, ith in enumerate((1, 2)):   # Om, w
+                ref = jac[key][:, ith]
+                assert _close(t[name][c], ref, rtol=1e-10, floor=max(1e-6, float(np.max(np.abs(ref))) * 1e-3))
+        for c, ith in enumerate((3, 4, 6, 7, 8)):   # a, b, mpisn, mbhmax, sigma
+            ref = jac["log_dN_grid"][:, ith]
+            assert _close(t["d_log_dN_grid"][c], ref, rtol=1e-10, floor=max(1e-6, float(np.max(np.abs(ref))) * 1e-3))
+        assert _close(sc[20:25], jac["log_pl_norm"][0, [3, 4, 6, 7, 8]], rtol=1e-10, floor=1e-3)
+        assert _close(sc[25:32], jac["log_norm"][0, [3, 4, 5, 6, 7, 8, 9]], rtol=1e-10, floor=1e-3)
+        assert _close(sc[32:34], jac["rate_log_norm"][0, [12, 13]], rtol=1e-10, floor=1e-3)
+    like.close()
+
+
+def test_cuda_matches_oracle_on_fresh_catalog(hl):
+    """A catalog that is NOT in the fixtures: ragged sizes (odd nsamp / nsel exercise the sentinel padding,
+    several tiles per event), 4 prior draws."""
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas, make_catalog
+    from oracle import bump_oracle as bo
+    cat = make_catalog("gwtc3", nobs=7, nsamp=3001, nsel=20001, seed=99)
+    like = hl(*cat.as_args())
+    for th in np.vstack([THETA_DEFAULT, draw_prior_thetas(4, seed=3)]):
+        r = like(th)
+        o = bo.evaluate(th, cat.as_args(), grad=True)
+        assert _close(r.loglike, o["loglike"]) and _close(r.log_mu_sel, o["log_mu_sel"])
+        assert _close(r.log_mu2, o["log_mu2"]) and _close(r.neff_sel, o["neff_sel"]) and _close(r.neff, o["neff"])
+        assert _close(r.dloglike, o["dloglike"], floor=max(1.0, float(np.max(np.abs(o["dloglike"])))))
+        assert _close(r.dlog_mu_sel, o["dlog_mu_sel"])
+    like.close()
+
+
+def test_wa_mode_matches_oracle(golden_dir, hl):
+    from oracle import bump_oracle as bo
+    g = _load(golden_dir, "tiny")
+    like = hl(*_data(g), wa=True)
+    for wa in (0.0, 0.4, -0.7):
+        th = np.concatenate([g["thetas"][1], [wa]])
+        r = like(th)
+        o = bo.evaluate(th[:14], _data(g), grad=True, wa=wa)
+        assert _close(r.loglike, o["loglike"]) and _close(r.log_mu_sel, o["log_mu_sel"])
+        assert _close(r.dloglike[:14], o["dloglike"], floor=max(1.0, float(np.max(np.abs(o["dloglike"])))))
+        assert _close(r.dlog_mu_sel[:14], o["dlog_mu_sel"])
+        assert _close(r.dloglike[14], o["dloglike_dwa"], floor=max(1.0, abs(o["dloglike_dwa"])))
+        assert _close(r.dlog_mu_sel[14], o["dlog_mu_sel_dwa"])
+    like.close()
+
+
+def test_edge_cases(hl):
+    """Samples beyond the last d_L knot, exactly on knots, below mbh_min; an event split over tiles;
+    one-sample events; a single injection."""
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
+    from oracle import bump_oracle as bo
+    cat = make_catalog("tiny", seed=5)
+    args = list(cat.as_args())
+    dls = args[2].copy()
+    dls[0, :4] = [5e3, 1e4, 1e-4, 2e-3]          # beyond z = 100 and tiny distances
+    m1 = args[0].copy()
+    m1[1, :8] = 4.0                               # below mbh_min -> -inf weights
+    args[2], args[0] = dls, m1
+    like = hl(*args)
+    o = bo.evaluate(THETA_DEFAULT, tuple(args), grad=True)
+    r = like(THETA_DEFAULT)
+    assert _close(r.loglike, o["loglike"]) and _close(r.neff, o["neff"])
+    assert _close(r.dloglike, o["dloglike"], floor=max(1.0, float(np.max(np.abs(o["dloglike"])))))
+    like.close()
+    # one sample per event, one injection
+    one = (args[0][:, :1], args[1][:, :1], args[2][:, 5:6], args[3][:, :1], args[4][:1], args[5][:1], args[6][:1],
+           args[7][:1], 10.0)
+    like = hl(*one)
+    o = bo.evaluate(THETA_DEFAULT, one, grad=True)
+    r = like(THETA_DEFAULT)
+    assert _close(r.loglike, o["loglike"]) and _close(r.log_mu_sel, o["log_mu_sel"])
+    assert _close(r.dlog_mu_sel, o["dlog_mu_sel"])
+    like.close()
+
+
+def test_partials_merge_equals_single_rank(hl):
+    """Emulate 3 ranks on one GPU: shard, evaluate partials, merge on the host (same code as the device
+    finalize) -> equals the unsharded evaluation to 1e-12."""
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
+    from bumpcosmology_b200.likelihood import merge_partials, shard_catalog, unpack_header
+    cat = make_catalog("small", seed=17)
+    full = hl(*cat.as_args())
+    r = full(THETA_DEFAULT)
+    parts, neffs = [], []
+    for rank in range(3):
+        sh = hl(*shard_catalog(cat.as_args(), rank, 3))
+        p, ne = sh.partial(THETA_DEFAULT)
+        parts.append(p)
+        neffs.append(ne)
+        sh.close()
+    m = unpack_header(merge_partials(np.array(parts)), 14)
+    assert _close(m["loglike"], r.loglike, rtol=1e-12) and _close(m["log_mu_sel"], r.log_mu_sel, rtol=1e-12)
+    assert _close(m["dloglike"], r.dloglike, rtol=1e-11, floor=max(1.0, float(np.max(np.abs(r.dloglike)))))
+    assert _close(m["dlog_mu_sel"], r.dlog_mu_sel, rtol=1e-11)
+    assert _close(np.concatenate(neffs), r.neff, rtol=1e-12)
+    full.close()
