@@ -16,7 +16,7 @@ OUT_DLOGLIKE, OUT_DLOG_MU = 4, 19
 OUT_NVALID_EVT, OUT_NVALID_SEL, OUT_NOBS, OUT_NSEL = 34, 35, 36, 37
 OUT_HEADER = 40
 PARTIAL_LEN = 128
-FLAG_WA, FLAG_NO_GRAPH = 1, 2
+FLAG_WA, FLAG_NO_GRAPH, FLAG_NO_SORT = 1, 2, 4
 
 _dp = C.POINTER(C.c_double)
 

@@ -90,6 +90,9 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
     const double iS = 1.0 / acc[0];
     for (int k = 0; k < NFEAT; ++k) phis[k] = acc[2 + k] * iS;
     grad_from_features(phis, 1.0, sc, out + OUT_DLOG_MU);
+    if (sc[S_BAD] != 0.0) {   // theta outside the support: the reference yields NaN (NUTS treats it as divergent)
+        for (int k = 0; k < OUT_NVALID_EVT; ++k) out[k] = NAN;
+    }
     out[OUT_NVALID_EVT] = nvalid_e;
     out[OUT_NVALID_SEL] = nvalid_s;
     out[OUT_NOBS] = nobs;

@@ -43,8 +43,10 @@ constexpr int SRCH_OCTAVES = 21;          // 2^-8 .. 2^13 Gpc
 constexpr int SRCH_N = SRCH_OCTAVES << SRCH_MBITS;   // 5376 uint16 entries
 constexpr int SRCH_DOUBLES = SRCH_N / 4;
 
+constexpr int NEXPT = 16;    // 2^(j/16), one 128-byte row of shared memory (bump_math.cuh fexp)
 constexpr int OFF_SCAL = 0;
-constexpr int OFF_COS = OFF_SCAL + NSCAL;               // double2 cos[NCPAIR][NZ]
+constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT]
+constexpr int OFF_COS = OFF_EXPT + NEXPT;               // double2 cos[NCPAIR][NZ]
 constexpr int OFF_CTAN = OFF_COS + NCPAIR * NZ * 2;     // double  ctan[NCTAN][NZ]
 constexpr int OFF_SRCH = OFF_CTAN + NCTAN * NZ;         // uint16  srch[SRCH_N]
 constexpr int OFF_MASS = OFF_SRCH + SRCH_DOUBLES;       // double2 mass[NMREC][NM]
@@ -52,6 +54,7 @@ constexpr int BLOB_DOUBLES = OFF_MASS + NMREC * NM * 2;
 constexpr int BLOB_BYTES = BLOB_DOUBLES * 8;
 static_assert(BLOB_BYTES % 16 == 0, "bulk copies need 16-byte multiples");
 static_assert(SRCH_N % 4 == 0, "search table must fill whole doubles");
+static_assert(OFF_EXPT % 16 == 0, "the exp table must sit on a 128-byte boundary");
 
 // cosmology pair records, bin b = [knot b, knot b+1]
 enum CosRec { CR_DL = 0,   // {dl_b, 1/(dl_{b+1}-dl_b)}
@@ -73,6 +76,10 @@ enum Scal {
     S_LOG_NSAMP = 34, S_LOG_NDRAW = 35, S_USE_WA = 36, S_DL_FIRST = 37,
     S_EXP_LPN = 38,  // fpl * exp(PISN(mbhmax)) = exp(log_pl_norm)
     S_ZEPS = 39,     // expm1(ZSTEP) = (z_{b+1}-z_b)/(1+z_b), the same for every bin of the log-uniform z grid
+    S_C2 = 40,       // 2 exp(log_pl_norm): prefactor of the power-law tail in linear space
+    S_LAM2 = 41,     // lam - 2
+    S_RATE0 = 42,    // lam - 3 - beta
+    S_BAD = 43,      // 1 if theta or any table entry is not finite (outputs are then NaN)
 };
 
 // ---- per-sample gradient features accumulated by the streaming kernel (DESIGN.md has the algebra)

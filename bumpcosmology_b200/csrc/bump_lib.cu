@@ -7,6 +7,7 @@
 //   [ncclAllGather of the 1 KiB partial when a communicator is attached]
 //   finalize_kernel  (bump_epilogue.cuh) rank-ordered merge, constants, chain rule -> result header
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -98,15 +99,32 @@ struct ColumnPtrs {
     double* c[NCOL];
 };
 
+// Locality key of a sample: (row | coarse d_L bucket | fine m1_det).  Sorting the samples of an event (the
+// likelihood is a sum over them, so their order is free) makes the 32 lanes of a warp land in the same or in
+// neighbouring bins of the d_L tables and of the mass table at m1: shared-memory reads become broadcasts /
+// conflict-free instead of random (DESIGN.md "sample order").
+__global__ void locality_keys_kernel(const double* __restrict__ m1d, const double* __restrict__ dl,
+                                     const int64_t ncols, const int64_t n, unsigned long long* __restrict__ keys,
+                                     unsigned int* __restrict__ idx) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long row = (unsigned long long)(i / ncols);
+        const unsigned int kd = ((unsigned int)__double2hiint(dl[i]) >> 15) & 0xFFFFu;        // 1/32-octave buckets
+        const unsigned int km = (unsigned int)min(max((__double2hiint(m1d[i]) - (1023 << 20)) >> 4, 0), 0xFFFFF);
+        keys[i] = (row << 36) | ((unsigned long long)kd << 20) | km;
+        idx[i] = (unsigned int)i;
+    }
+}
+
 __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const double* __restrict__ q,
                                        const double* __restrict__ dl, const double* __restrict__ pd,
-                                       const int64_t nrows, const int64_t ncols, const int64_t stride,
-                                       ColumnPtrs out) {
+                                       const unsigned int* __restrict__ perm, const int64_t nrows,
+                                       const int64_t ncols, const int64_t stride, ColumnPtrs out) {
     const int64_t total = nrows * stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / stride, c = i - r * stride;
         if (c < ncols) {
-            const int64_t s = r * ncols + c;
+            int64_t s = r * ncols + c;
+            if (perm) s = perm[s];
             const double vm = m1d[s], vq = q[s];
             out.c[C_DL][i] = dl[s];
             out.c[C_M1D][i] = vm;
@@ -199,10 +217,27 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     ColumnPtrs cp;
     for (int k = 0; k < NCOL; ++k) cp.c[k] = ds.col(k);
     const int blocks = (int)std::min<int64_t>((npad + 255) / 256, 148 * 16);
-    prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, nrows, ncols,
+    unsigned int* perm = nullptr;
+    unsigned long long *keys = nullptr, *keys_out = nullptr;
+    unsigned int* idx = nullptr;
+    void* tmp = nullptr;
+    const bool sort = !(c->flags & BUMP_FLAG_NO_SORT) && n > 64 && n < (int64_t(1) << 32) && nrows < (int64_t(1) << 27);
+    if (sort) {
+        CK(cudaMalloc(&keys, sizeof(unsigned long long) * n));
+        CK(cudaMalloc(&keys_out, sizeof(unsigned long long) * n));
+        CK(cudaMalloc(&idx, sizeof(unsigned int) * n));
+        CK(cudaMalloc(&perm, sizeof(unsigned int) * n));
+        locality_keys_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + 2 * n, ncols, n, keys, idx);
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, perm, n, 0, 64, c->stream));
+        CK(cudaMalloc(&tmp, tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, idx, perm, n, 0, 64, c->stream));
+    }
+    prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, perm, nrows, ncols,
                                                           ds.stride, cp);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp), cudaFree(keys), cudaFree(keys_out), cudaFree(idx), cudaFree(perm);
     CK(cudaFree(raw));
     return BUMP_OK;
 }

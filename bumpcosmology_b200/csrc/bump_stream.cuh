@@ -1,10 +1,18 @@
-// The streaming kernel: one pass over the SoA sample / injection columns producing, per tile, the
-// max-shifted sums  S = sum e^{w-m},  S2 = sum e^{2(w-m)}  and the 16 gradient features  sum e^{w-m} f_k.
+// The streaming kernel: one pass over the SoA sample / injection columns producing, per tile, the shifted sums
+//   S = sum e^{w-m},  S2 = sum e^{2(w-m)}  and the 17 gradient features  sum e^{w-m} f_k.
 //
 // Replaces intensity_models.py:378-381 (events) and :385-388 (injections) — z_of_dL, detector->source masses,
 // LogDNDMDQDV.__call__ (:202-210), LogDNDM.__call__ (:140-151), log_smooth_turnon (:45-54), LogDNDV.__call__
 // (:170-173), the Jacobian terms — plus the inner part of the logsumexp reductions (:382,389,392,401) and the
 // reverse pass of all of it, in forward mode.
+//
+// Arithmetic is organised in LINEAR space: the weight of a sample is the product
+//   p = e^{w-m} = (e^{P(m1)} + e^{Q(m1)}) (e^{P(m2)} + e^{Q(m2)}) * dVc/dz / (d dL/dz) / (1+r) * e^{lin-m}
+// where lin collects every term that is linear in precomputed logs, so a sample costs 8 exp, 4 reciprocals
+// and NO logarithm; softmax-weighted gradient terms are products of the same factors (no divisions).
+// The shift m is per thread: the `lin` of its first finite-weight sample, raised only when a later sample
+// exceeds it by e^RESCALE_GAP (fp64 has the range to carry everything else); threads and tiles are merged
+// with the usual (max, rescale) rule, so the result equals the reference's max-shifted logsumexp.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -19,7 +27,7 @@ namespace bump {
 constexpr int STREAM_THREADS = BUMP_STREAM_THREADS;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/ + STREAM_WARPS * (NACC + 2) * 8;
-constexpr double RESCALE_GAP = 60.0;   // rescale the running shift when a weight exceeds it by e^60
+constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,60 +63,76 @@ __device__ __forceinline__ void stage_tables(double* s_blob, uint64_t* mbar, con
     }
 }
 
-struct SampleOut {
-    double w;          // log weight without the theta-only constant; -inf if the sample carries no weight
-    double f[NFEAT];
+struct ThreadAcc {
+    double m;           // shift
+    double a[NACC];     // S, S2, features
+    int nvalid;
 };
 
-// One mass-function evaluation A0(m) = logaddexp(P(m), Q(m)) and its feature contributions.
-__device__ __forceinline__ double mass_term(const double m, const double lm, const double* __restrict__ sc,
-                                            const double2* __restrict__ mass, double (&f)[NFEAT], double& mdA) {
-    const double M = sc[S_M], c = sc[S_C];
-    // power-law tail with smooth turn-on, :147 and :45-54
-    const double y = (m - M) * sc[S_INV_DM];
-    const double e = fexp(-y);
+__device__ __forceinline__ void acc_init(ThreadAcc& A) {
+    A.m = -INFINITY;
+    A.nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) A.a[k] = 0.0;
+}
+
+// One mass-function evaluation in linear space: e^{A0(m)} = EP + EQ with EP = e^{PISN(m)} (:110-111,144-145),
+// EQ = e^{-c log(m/mbhmax) + log_pl_norm + turnon(m)} (:147, :45-54).
+struct MassEval {
+    double EP, EQ;   // the two terms of the logaddexp, in linear space
+    double lrel;     // log(m / mbhmax)
+    double sgm;      // m * e/(1+e) : m times the turn-on's logistic weight
+    double slope;    // dP/dm inside the bin
+    double m, u;
+    int b;
+};
+
+__device__ __forceinline__ void mass_eval(const double m, const double lm, const double* __restrict__ sc,
+                                          const double2* __restrict__ mass, const double* __restrict__ expt,
+                                          MassEval& o) {
+    const double y = (m - sc[S_M]) * sc[S_INV_DM];
+    const double e = fexp(-y, expt);
     const double s1 = frcp(1.0 + e);
-    const double sg = e * s1;                       // e/(1+e)
-    const double turn = LN2 + flog(s1);             // log 2 - log1p(e)
-    const double lrel = lm - sc[S_LOG_M];
-    const double Q = fma(-c, lrel, sc[S_LPN] + turn);
-    // PISN table lookup (:110-111) with the -inf guards of :144-145 (m <= 3 cannot happen once m >= 5)
-    const bool inP = m < sc[S_TOP];
+    o.sgm = (e * s1) * m;
+    o.lrel = lm - sc[S_LOG_M];
+    o.EQ = fexp(-sc[S_C] * o.lrel, expt) * (sc[S_C2] * s1);
     const double pos = (m - MIN_BH_MASS) * sc[S_INV_DMBH];
     int b = __double2int_rd(pos);
     b = min(max(b, 0), NM - 2);
-    const double u = pos - (double)b;
+    o.u = pos - (double)b;
     const double2 g = mass[MR_G * NM + b];
-    const double P = fma(u, g.y, g.x);
-    // logaddexp(P, Q)
-    const double d = inP ? (P - Q) : -INFINITY;
-    const double E = fexp(-fabs(d));
-    const double s = frcp(1.0 + E);
-    const double Es = E * s;
-    const double sP = (d > 0.0) ? s : Es;
-    const double sQ = (d > 0.0) ? Es : s;
-    const double A0 = ((d > 0.0) ? P : Q) - flog(s);
-    // features
-    const double slope = g.y * sc[S_INV_DMBH];       // dP/dm
-    const double dT = sg * sc[S_INV_DM];             // d turn / dm
-    mdA = sP * slope * m + sQ * fma(dT, m, -c);      // m * dA0/dm
-    f[F_SQ] += sQ;
-    f[F_C] = fma(sQ, lrel, f[F_C]);
+    const double eP = fexp(fma(o.u, g.y, g.x), expt);
+    o.EP = (m < sc[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
+    o.slope = g.y * sc[S_INV_DMBH];
+    o.m = m;
+    o.b = b;
+}
+
+// Feature contributions of one mass evaluation, weighted by wp = (weight of the sample) / (EP + EQ).
+__device__ __forceinline__ double mass_features(const MassEval& o, const double wp, const double* __restrict__ sc,
+                                                const double2* __restrict__ mass, double* __restrict__ a) {
+    const double wQ = wp * o.EQ, wP = wp * o.EP;
+    a[2 + F_SQ] += wQ;
+    a[2 + F_C] = fma(wQ, o.lrel, a[2 + F_C]);
+    const double wQs = wQ * o.sgm;                         // wQ * m * logistic
+    a[2 + F_T] += wQs;
+    const double wPs = wP * o.slope;
+    a[2 + F_GEO] = fma(wPs, o.m - MIN_BH_MASS, a[2 + F_GEO]);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const double2 t = mass[(MR_GA + k) * NM + b];
-        f[F_PA + k] = fma(sP, fma(u, t.y, t.x), f[F_PA + k]);
+        const double2 t = mass[(MR_GA + k) * NM + o.b];
+        a[2 + F_PA + k] = fma(wP, fma(o.u, t.y, t.x), a[2 + F_PA + k]);
     }
-    f[F_GEO] = fma(sP * slope, m - MIN_BH_MASS, f[F_GEO]);
-    f[F_T] = fma(sQ * sg, m, f[F_T]);
-    return A0;
+    // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c)
+    return fma(wPs, o.m, fma(wQs, sc[S_INV_DM], -sc[S_C] * wQ));
 }
 
 template <bool WA>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
-                                            const double* __restrict__ s_blob, SampleOut& o) {
+                                            const double* __restrict__ s_blob, ThreadAcc& A) {
     const double* __restrict__ sc = s_blob + OFF_SCAL;
+    const double* __restrict__ expt = s_blob + OFF_EXPT;
     const double2* __restrict__ cos = reinterpret_cast<const double2*>(s_blob + OFF_COS);
     const double* __restrict__ ctan = s_blob + OFF_CTAN;
     const unsigned short* __restrict__ srch = reinterpret_cast<const unsigned short*>(s_blob + OFF_SRCH);
@@ -132,91 +156,77 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double u1 = frcp1p_small(te);
     const double ropz = rz.x * u1;                  // 1/(1+z)
     const double L = rz.y + flog1p_small(te);       // log1p(z)
-    const double lt = zeps * u1;                    // dL/dt
     // ---- source-frame masses (:379, :207)
     double m1 = m1d * ropz;
     double m2 = q * m1;
     double lm1 = lm - L;
     double lm2 = lm1 + lq;
-    bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);   // :149
-    if (!valid) {   // keep every intermediate finite; the sample gets zero weight below
-        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
-    }
     // ---- dVC/dz and d(dL)/dz lerps at z (:264-268), same bin, same t
     const double2 rvc = cos[CR_DVC * NZ + b];
     const double2 rdd = cos[CR_DDL * NZ + b];
     const double dvc = fma(t, rvc.y, rvc.x);
     const double ddl = fma(t, rdd.y, rdd.x);
-    valid = valid && (dvc > 0.0);
-    const double idvc = frcp(valid ? dvc : 1.0);
+    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN) && (dvc > 0.0);   // :149; log(dVc/dz = 0) = -inf
+    if (!valid) {   // keep every intermediate finite; the sample gets exactly zero weight below
+        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
+    }
     const double iddl = frcp(ddl);
-    const double ljac = flog((valid ? dvc : 1.0) * iddl);
-    // ---- merger-rate density (:173)
-    const double lam = sc[S_LAM], kappa = sc[S_KAPPA], beta = sc[S_BETA];
-    const double r = fexp(kappa * (L - sc[S_LOPZP]));
+    // ---- everything that is linear in precomputed logs: beta log(m1+m2) + log m1 + (lam-2) log1p(z) - log pdraw
+    const double pair = lm1 + l1q;                  // log(m1+m2); the -beta log(60) is in the constant
+    const double lin = fma(sc[S_BETA], pair, lm1) + fma(sc[S_LAM2], L, -lpd);
+    if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
+        A.a[0] *= s;
+        A.a[1] *= s * s;
+#pragma unroll
+        for (int k = 2; k < NACC; ++k) A.a[k] *= s;
+        A.m = lin;
+    }
+    const double E = valid ? fexp(lin - A.m, expt) : 0.0;
+    A.nvalid += valid ? 1 : 0;
+    // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
+    const double kappa = sc[S_KAPPA];
+    const double r = fexp(kappa * (L - sc[S_LOPZP]), expt);
     const double sr = frcp(1.0 + r);
     const double sig = r * sr;
-    const double V0 = fma(lam, L, flog(sr));        // lam*log1p(z) - log1p(r)
-#pragma unroll
-    for (int k = 0; k < NFEAT; ++k) o.f[k] = 0.0;
-    double mdA1, mdA2;
-    const double A1 = mass_term(m1, lm1, sc, mass, o.f, mdA1);
-    const double A2 = mass_term(m2, lm2, sc, mass, o.f, mdA2);
-    const double pair = lm1 + l1q;                  // log(m1+m2); the -log(60) is in the constant
-    double w = A1 + A2 + fma(beta, pair, lm1) + V0 - 2.0 * L + ljac - lpd;   // :210, :381
-    // ---- d w / d t at fixed tables, then the cosmological tangents
-    const double Wt = lt * (lam - kappa * sig - 3.0 - beta - mdA1 - mdA2) + rvc.y * idvc - rdd.y * iddl;
-    const double Wx = Wt * idl;                     // -Wx * (d dl-table / d theta)(t) = (dw/dt)(dt/dtheta)
-    o.f[F_CZ] = Wx * x;
-    auto tangent = [&](const int tdl, const int tdvc, const int tddl) -> double {
+    // ---- mass function at both masses
+    MassEval M1, M2;
+    mass_eval(m1, lm1, sc, mass, expt, M1);
+    mass_eval(m2, lm2, sc, mass, expt, M2);
+    const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
+    // ---- the weight and its partial products
+    const double base = (sr * iddl) * E;            // everything but the masses and dVc/dz
+    const double p0 = (sum1 * sum2) * base;         // weight / (dVc/dz)
+    const double p = p0 * dvc;                      // e^{w - m}   (:381 / :388)
+    const double bv = base * dvc;
+    A.a[0] += p;
+    A.a[1] = fma(p, p, A.a[1]);
+    const double md = mass_features(M1, sum2 * bv, sc, mass, A.a) + mass_features(M2, sum1 * bv, sc, mass, A.a);
+    // ---- d w / d t at fixed tables (times p), then the cosmological tangents
+    const double lt = zeps * u1;                    // d log1p(z) / dt
+    const double psig = p * sig;
+    const double pWt = fma(lt, fma(p, sc[S_RATE0], -fma(kappa, psig, md)), fma(rvc.y, p0, -(rdd.y * iddl) * p));
+    const double pWx = pWt * idl;                   // -pWx * (d dl-table/d theta)(t) = p (dw/dt)(dt/dtheta)
+    A.a[2 + F_CZ] = fma(pWx, x, A.a[2 + F_CZ]);
+    const double pid = p * iddl;
+    auto tangent = [&](const int tdl, const int tdvc, const int tddl, double& acc) {
         const double a0 = ctan[tdl * NZ + b], a1 = ctan[tdl * NZ + b + 1];
         const double v0 = ctan[tdvc * NZ + b], v1 = ctan[tdvc * NZ + b + 1];
         const double d0 = ctan[tddl * NZ + b], d1 = ctan[tddl * NZ + b + 1];
-        return fma(-Wx, fma(t, a1 - a0, a0), fma(t, v1 - v0, v0) * idvc - fma(t, d1 - d0, d0) * iddl);
+        acc = fma(-pWx, fma(t, a1 - a0, a0), fma(p0, fma(t, v1 - v0, v0), fma(-pid, fma(t, d1 - d0, d0), acc)));
     };
-    o.f[F_OM] = tangent(CT_DL_OM, CT_DVC_OM, CT_DDL_OM);
-    o.f[F_W] = tangent(CT_DL_W, CT_DVC_W, CT_DDL_W);
-    if constexpr (WA) o.f[F_WA] = tangent(CT_DL_WA, CT_DVC_WA, CT_DDL_WA);
-    o.f[F_BETA] = pair;
-    o.f[F_L] = L;
-    o.f[F_SIG] = sig;
-    o.f[F_SIGL] = sig * L;
-    o.w = valid ? w : -INFINITY;
+    tangent(CT_DL_OM, CT_DVC_OM, CT_DDL_OM, A.a[2 + F_OM]);
+    tangent(CT_DL_W, CT_DVC_W, CT_DDL_W, A.a[2 + F_W]);
+    if constexpr (WA) tangent(CT_DL_WA, CT_DVC_WA, CT_DDL_WA, A.a[2 + F_WA]);
+    A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
+    A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
+    A.a[2 + F_SIG] += psig;
+    A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
 }
 
-struct ThreadAcc {
-    double m;           // running shift (max-like)
-    double a[NACC];     // S, S2, features
-    double nvalid;
-};
-
-__device__ __forceinline__ void acc_init(ThreadAcc& A) {
-    A.m = -INFINITY;
-    A.nvalid = 0.0;
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) A.a[k] = 0.0;
-}
-
-__device__ __forceinline__ void acc_add(ThreadAcc& A, const SampleOut& o) {
-    if (o.w == -INFINITY) return;
-    if (o.w - A.m > RESCALE_GAP) {   // also the first finite sample (m = -inf)
-        const double sc = (A.m == -INFINITY) ? 0.0 : fexp(A.m - o.w);
-        A.a[0] *= sc;
-        A.a[1] *= sc * sc;
-#pragma unroll
-        for (int k = 2; k < NACC; ++k) A.a[k] *= sc;
-        A.m = o.w;
-    }
-    const double p = fexp(o.w - A.m);
-    A.a[0] += p;
-    A.a[1] = fma(p, p, A.a[1]);
-#pragma unroll
-    for (int k = 0; k < NFEAT; ++k) A.a[2 + k] = fma(p, o.f[k], A.a[2 + k]);
-    A.nvalid += 1.0;
-}
-
-// Block-wide merge of the per-thread accumulators, deterministic order; result written by thread 0..NACC+1.
-__device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* __restrict__ out) {
+// Block-wide merge of the per-thread accumulators, deterministic order; result written by threads 0..NACC+1.
+__device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* __restrict__ out,
+                                            const double* __restrict__ expt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double mx = A.m;
 #pragma unroll
@@ -227,7 +237,7 @@ __device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* _
     mx = red[0];
 #pragma unroll
     for (int w = 1; w < STREAM_WARPS; ++w) mx = fmax(mx, red[w]);
-    const double sc = (A.m == -INFINITY) ? 0.0 : fexp(A.m - mx);
+    const double sc = (A.m == -INFINITY) ? 0.0 : exp(A.m - mx);
     A.a[0] *= sc;
     A.a[1] *= sc * sc;
 #pragma unroll
@@ -235,7 +245,7 @@ __device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* _
     double v[NACC + 1];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) v[k] = A.a[k];
-    v[NACC] = A.nvalid;
+    v[NACC] = (double)A.nvalid;
 #pragma unroll
     for (int k = 0; k <= NACC; ++k) {
 #pragma unroll
@@ -284,13 +294,10 @@ stream_kernel(const Columns cols, const Tile* __restrict__ tiles, const int ntil
         for (int p = threadIdx.x; p < npairs; p += STREAM_THREADS) {
             const double2 dl = __ldg(c_dl + p), m1 = __ldg(c_m1 + p), q = __ldg(c_q + p), lm = __ldg(c_lm + p),
                           lq = __ldg(c_lq + p), l1q = __ldg(c_l1q + p), lpd = __ldg(c_lpd + p);
-            SampleOut o;
-            eval_sample<WA>(dl.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, o);
-            acc_add(A, o);
-            eval_sample<WA>(dl.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, o);
-            acc_add(A, o);
+            eval_sample<WA>(dl.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, A);
+            eval_sample<WA>(dl.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, A);
         }
-        tile_reduce(A, red, part + (size_t)tile * PART_STRIDE);
+        tile_reduce(A, red, part + (size_t)tile * PART_STRIDE, s_blob + OFF_EXPT);
     }
 }
 

@@ -276,6 +276,9 @@ __device__ void build_scalars(const double* th, const double* aux_, const EvalCo
     scal[S_DL_FIRST] = aux[AUX_DL + 0];
     scal[S_EXP_LPN] = exp(lpn.v);
     scal[S_ZEPS] = expm1(ZSTEP);
+    scal[S_C2] = 2.0 * exp(lpn.v);
+    scal[S_LAM2] = th[T_LAM] - 2.0;
+    scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
 
 __device__ void build_records(const double* aux_, int use_wa, double* blob) {
@@ -341,8 +344,18 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     if (!is_last) return;
     __threadfence();
     build_records(aux, ec.use_wa, blob);
+    if (threadIdx.x < NEXPT) blob[OFF_EXPT + threadIdx.x] = exp2((double)threadIdx.x / NEXPT);
+    // non-finite theta or tables (theta outside the prior support): flag it, finalize returns NaN
+    int bad = 0;
+    {
+        const CgView a{aux};
+        for (int i = threadIdx.x; i < AUX_DOUBLES; i += blockDim.x) bad |= !isfinite(a[i]);
+        if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
+    }
+    bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
         build_scalars(th, aux, ec, blob + OFF_SCAL);
+        blob[OFF_SCAL + S_BAD] = bad ? 1.0 : 0.0;
         *ticket = 0u;
     }
 }

@@ -84,13 +84,14 @@ class Hyperlikelihood:
     """
 
     def __init__(self, m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, device=0,
-                 wa=False, graph=True):
+                 wa=False, graph=True, sort=True):
         self.lib = _lib.load()
         self.wa = bool(wa)
         self.ntheta = _lib.NTHETA_MAX if wa else _lib.NTHETA
         self.device = int(device)
         self._ctx = C.c_void_p()
-        flags = (_lib.FLAG_WA if wa else 0) | (0 if graph else _lib.FLAG_NO_GRAPH)
+        flags = ((_lib.FLAG_WA if wa else 0) | (0 if graph else _lib.FLAG_NO_GRAPH)
+                 | (0 if sort else _lib.FLAG_NO_SORT))
         _lib.check(self.lib.bump_ctx_create(C.byref(self._ctx), self.device, flags))
         ev = [_c64(x) for x in (m1s_det, qs, dls, pdraw)]
         if ev[0].ndim == 1:

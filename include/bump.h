@@ -48,6 +48,7 @@ extern "C" {
 /* Evaluation flags (bump_ctx_create). */
 #define BUMP_FLAG_WA 1u        /* w0-wa (CPL) dark energy: theta has 15 entries */
 #define BUMP_FLAG_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
+#define BUMP_FLAG_NO_SORT 4u   /* keep the caller's sample order inside each event (default: locality sort at upload) */
 
 typedef struct bump_ctx bump_ctx;
 

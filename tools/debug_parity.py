@@ -1,6 +1,6 @@
 """Debug helper (not a test): print CUDA-vs-golden differences."""
 import os, sys, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bumpcosmology_b200.likelihood import Hyperlikelihood
 from oracle import bump_oracle as bo
 np.set_printoptions(linewidth=200, precision=4)
