@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbump_b200.so")
+LIB_PATH = os.environ.get("BUMP_LIB_PATH", os.path.join(_PKG, "libbump_b200.so"))   # override: tuning builds only
 
 NTHETA = 14
 NTHETA_MAX = 15

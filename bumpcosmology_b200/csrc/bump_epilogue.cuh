@@ -139,15 +139,21 @@ __device__ __forceinline__ void epi_block_sum(double (&v)[NV], double* red) {
     }
 }
 
-// One block.  part: [ntiles][PART_STRIDE]; event e owns tiles [evt_tile_begin[e], evt_tile_begin[e+1]);
-// injection tiles are [n_evt_tiles, n_evt_tiles + n_sel_tiles).
+// Record index of (warp w, event e): warp w's records start at rec_off[w] and are ordered by event.
+__device__ __forceinline__ size_t record_of(const Work& wk, const int* __restrict__ rec_off, const int64_t w,
+                                            const int64_t e) {
+    return (size_t)rec_off[w] + (size_t)(e - group_event(wk, w * wk.gpw));
+}
+
+// One block.  part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt))
+// is covered by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
 __global__ void __launch_bounds__(EPI_THREADS)
-epilogue_kernel(const double* __restrict__ part, const int* __restrict__ evt_tile_begin, const int nobs,
-                const int n_evt_tiles, const int n_sel_tiles, const double nsel, const double* __restrict__ blob,
-                double* __restrict__ neff_out, double* __restrict__ partial) {
+epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off, const Work wk, const double nsel,
+                const double* __restrict__ blob, double* __restrict__ neff_out, double* __restrict__ partial) {
     __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
     __shared__ double s_max;
     const int tid = threadIdx.x;
+    const int nobs = wk.nobs;
     // ---- events
     double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
 #pragma unroll
@@ -156,8 +162,9 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ evt_til
         double m = -INFINITY, a[NACC], nv = 0.0;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) a[k] = 0.0;
-        for (int t = evt_tile_begin[e]; t < evt_tile_begin[e + 1]; ++t) {
-            const double* p = part + (size_t)t * PART_STRIDE;
+        const int64_t w0 = (e * wk.g_evt) / wk.gpw, w1 = ((e + 1) * wk.g_evt - 1) / wk.gpw;
+        for (int64_t w = w0; w <= w1; ++w) {
+            const double* p = part + record_of(wk, rec_off, w, e) * PART_STRIDE;
             double b[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) b[k] = p[1 + k];
@@ -177,9 +184,13 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ evt_til
         for (int k = 0; k < NFEAT; ++k) ev[3 + k] += a[2 + k] * iS;
     }
     epi_block_sum<NFEAT + 3>(ev, red);
-    // ---- injections: global shift first, then plain sums
+    // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps that own its groups
+    const bool has_sel = wk.n_groups > wk.n_evt_groups;
+    const int64_t ws0 = has_sel ? wk.n_evt_groups / wk.gpw : 0;
+    const int64_t ws1 = has_sel ? (wk.n_groups - 1) / wk.gpw : -1;
     double mx = -INFINITY;
-    for (int t = tid; t < n_sel_tiles; t += EPI_THREADS) mx = fmax(mx, part[(size_t)(n_evt_tiles + t) * PART_STRIDE]);
+    for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS)
+        mx = fmax(mx, part[record_of(wk, rec_off, w, nobs) * PART_STRIDE]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     __syncthreads();
@@ -195,8 +206,8 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ evt_til
     double sv[NACC + 1];
 #pragma unroll
     for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
-    for (int t = tid; t < n_sel_tiles; t += EPI_THREADS) {
-        const double* p = part + (size_t)(n_evt_tiles + t) * PART_STRIDE;
+    for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
+        const double* p = part + record_of(wk, rec_off, w, nobs) * PART_STRIDE;
         if (p[0] == -INFINITY) continue;
         const double s = exp(p[0] - mx);
         sv[0] += p[1] * s;

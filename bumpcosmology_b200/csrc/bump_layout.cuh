@@ -87,21 +87,35 @@ enum Feat { F_CZ = 0, F_OM, F_W, F_SQ, F_C, F_PA, F_PB, F_PMPISN, F_PMBHMAX, F_P
             F_SIG, F_SIGL, F_WA, NFEAT };
 static_assert(NFEAT == 17, "17 features");
 constexpr int NACC = 2 + NFEAT;   // S, S2, features
-constexpr int PART_STRIDE = 24;   // per-tile partial: [0] shift m, [1..19] acc, [20] nvalid
+constexpr int PART_STRIDE = 24;   // per-record partial: [0] shift m, [1..19] acc, [20] nvalid
 
-// ---- tiles
-struct Tile {
-    int64_t off;   // first sample (index into the padded column arrays of its set); even
-    int32_t count; // samples in the tile (even; may include sentinel padding)
-    int32_t set;   // 0 = events, 1 = injections
+// ---- work decomposition of the streaming kernel: the unit is a GROUP of 64 consecutive samples of one event
+// (or of the injection set), two samples per lane.  Groups are numbered events-first; every warp of the grid owns
+// one contiguous, equally long range of groups and writes one RECORD per event it touches (plus one for the
+// injection set), so events never need a block-wide reduction and no warp waits for another.
+constexpr int GROUP = 64;
+struct Work {
+    int64_t g_evt;         // groups per event  = ceil(evt_stride / GROUP)
+    int64_t n_evt_groups;  // nobs * g_evt
+    int64_t n_groups;      // + groups of the injection set
+    int64_t gpw;           // groups per warp (last warps may own fewer / none)
+    int64_t evt_stride;    // padded samples per event (even)
+    int64_t sel_stride;    // padded injections (even)
+    int32_t nobs;
+    int32_t nwarps;
 };
+// event id of a group (the injection set is pseudo-event `nobs`)
+__host__ __device__ inline int64_t group_event(const Work& w, const int64_t g) {
+    return g < w.n_evt_groups ? g / w.g_evt : (int64_t)w.nobs;
+}
 
 constexpr int NCOL = 7;  // dl, m1det, q, log m1det, log q, log1p q, log pdraw
 enum Col { C_DL = 0, C_M1D, C_Q, C_LM, C_LQ, C_L1Q, C_LPD };
 
-struct Columns {
-    const double* evt[NCOL];
-    const double* sel[NCOL];
+struct Columns {   // column k of a set = base + k * pitch (one allocation per set)
+    const double* evt_base;
+    const double* sel_base;
+    int64_t evt_pitch, sel_pitch;
 };
 
 // ---- per-rank partial (multi-GPU exchange); doubles

@@ -162,9 +162,9 @@ struct bump_ctx {
     double ndraw = 1.0;
     // plan
     bool plan_dirty = true;
-    int ntiles = 0, n_evt_tiles = 0, n_sel_tiles = 0, grid = 0, sm_count = 0;
-    Tile* d_tiles = nullptr;
-    int* d_evt_tile_begin = nullptr;
+    Work work{};
+    int nrecords = 0, grid = 0, sm_count = 0;
+    int* d_rec_off = nullptr;
     double* d_part = nullptr;
     // workspaces
     double *d_theta = nullptr, *d_aux = nullptr, *d_blob = nullptr, *d_partial = nullptr, *d_gather = nullptr,
@@ -188,8 +188,7 @@ int set_device(const bump_ctx* c) {
 
 void free_plan(bump_ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
-    cudaFree(c->d_tiles), c->d_tiles = nullptr;
-    cudaFree(c->d_evt_tile_begin), c->d_evt_tile_begin = nullptr;
+    cudaFree(c->d_rec_off), c->d_rec_off = nullptr;
     cudaFree(c->d_part), c->d_part = nullptr;
     cudaFree(c->d_out), c->d_out = nullptr;
     if (c->h_out) cudaFreeHost(c->h_out), c->h_out = nullptr;
@@ -242,58 +241,45 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     return BUMP_OK;
 }
 
-// Split [0, n) (n even) into k chunks of even size, nearly equal.
-void split_even(int64_t base, int64_t n, int k, int set, std::vector<Tile>& tiles) {
-    const int64_t pairs = n / 2;
-    for (int i = 0; i < k; ++i) {
-        const int64_t lo = pairs * i / k, hi = pairs * (i + 1) / k;
-        if (hi > lo) tiles.push_back(Tile{base + 2 * lo, (int32_t)(2 * (hi - lo)), set});
-    }
-}
-
 int build_plan(bump_ctx* c) {
     if (int r = set_device(c)) return r;
     free_plan(c);
-    const int64_t ntot = c->evt.nrows * c->evt.stride + c->sel.nrows * c->sel.stride;
-    // tile size: aim at >= 4 tiles per SM, bounded so the per-tile block reduction stays a small fraction
-    int64_t target = (ntot / (4LL * c->sm_count) + 255) / 256 * 256;
-    target = std::min<int64_t>(std::max<int64_t>(target, 1024), 12288);
-    if (const char* e = getenv("BUMP_TILE")) target = std::max<int64_t>(256, atoll(e) / 2 * 2);
-    std::vector<Tile> tiles;
-    std::vector<int> begin(c->evt.nrows + 1, 0);
-    for (int64_t e = 0; e < c->evt.nrows; ++e) {
-        begin[e] = (int)tiles.size();
-        const int k = (int)std::max<int64_t>(1, (c->evt.stride + target - 1) / target);
-        split_even(e * c->evt.stride, c->evt.stride, k, 0, tiles);
+    Work& w = c->work;
+    w.nobs = (int32_t)c->evt.nrows;
+    w.evt_stride = c->evt.stride;
+    w.sel_stride = c->sel.nrows ? c->sel.stride : 0;
+    w.g_evt = std::max<int64_t>(1, (w.evt_stride + GROUP - 1) / GROUP);
+    w.n_evt_groups = w.nobs * w.g_evt;
+    w.n_groups = w.n_evt_groups + (w.sel_stride + GROUP - 1) / GROUP;
+    // one CTA per SM (persistent); use fewer CTAs only when there are fewer groups than warps
+    const int64_t max_warps = (int64_t)c->sm_count * STREAM_WARPS;
+    if (const char* e = getenv("BUMP_GPW")) w.gpw = std::max<int64_t>(1, atoll(e));
+    else w.gpw = std::max<int64_t>(1, (w.n_groups + max_warps - 1) / max_warps);
+    w.nwarps = (int32_t)std::max<int64_t>(1, (w.n_groups + w.gpw - 1) / w.gpw);
+    c->grid = (w.nwarps + STREAM_WARPS - 1) / STREAM_WARPS;
+    std::vector<int> rec_off(w.nwarps + 1, 0);
+    for (int i = 0; i < w.nwarps; ++i) {
+        const int64_t g0 = (int64_t)i * w.gpw, g1 = std::min(g0 + w.gpw, w.n_groups);
+        const int n = g0 < g1 ? (int)(group_event(w, g1 - 1) - group_event(w, g0) + 1) : 0;
+        rec_off[i + 1] = rec_off[i] + n;
     }
-    begin[c->evt.nrows] = (int)tiles.size();
-    c->n_evt_tiles = (int)tiles.size();
-    if (c->sel.nrows * c->sel.stride > 0) {
-        const int k = (int)std::max<int64_t>(1, (c->sel.stride + target - 1) / target);
-        split_even(0, c->sel.stride, k, 1, tiles);
-    }
-    c->ntiles = (int)tiles.size();
-    c->n_sel_tiles = c->ntiles - c->n_evt_tiles;
-    c->grid = std::max(1, std::min(c->ntiles, c->sm_count));
+    c->nrecords = rec_off[w.nwarps];
     c->out_len = OUT_HEADER + c->evt.nrows;
-    CK(cudaMalloc(&c->d_tiles, sizeof(Tile) * std::max<size_t>(1, tiles.size())));
-    CK(cudaMalloc(&c->d_evt_tile_begin, sizeof(int) * begin.size()));
-    CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max<size_t>(1, tiles.size())));
+    CK(cudaMalloc(&c->d_rec_off, sizeof(int) * rec_off.size()));
+    CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max(1, c->nrecords)));
     CK(cudaMalloc(&c->d_out, sizeof(double) * c->out_len));
     CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
-    if (!tiles.empty())
-        CK(cudaMemcpy(c->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_evt_tile_begin, begin.data(), sizeof(int) * begin.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size(), cudaMemcpyHostToDevice));
     c->plan_dirty = false;
     return BUMP_OK;
 }
 
 Columns columns_of(const bump_ctx* c) {
     Columns cols;
-    for (int k = 0; k < NCOL; ++k) {
-        cols.evt[k] = c->evt.base ? c->evt.col(k) : nullptr;
-        cols.sel[k] = c->sel.base ? c->sel.col(k) : nullptr;
-    }
+    cols.evt_base = c->evt.base;
+    cols.sel_base = c->sel.base;
+    cols.evt_pitch = c->evt.nrows * c->evt.stride;
+    cols.sel_pitch = c->sel.nrows * c->sel.stride;
     return cols;
 }
 
@@ -310,17 +296,17 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr) {
     prologue_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket, consts_of(c));
     if (k0) cudaEventRecord(k0, s);
-    if (c->ntiles > 0) {
+    if (c->work.n_groups > 0) {
         if (c->use_wa)
-            stream_kernel<true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->d_tiles, c->ntiles,
+            stream_kernel<true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work, c->d_rec_off,
                                                                                    c->d_blob, c->d_part);
         else
-            stream_kernel<false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->d_tiles,
-                                                                                    c->ntiles, c->d_blob, c->d_part);
+            stream_kernel<false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work,
+                                                                                    c->d_rec_off, c->d_blob, c->d_part);
     }
     if (k1) cudaEventRecord(k1, s);
-    epilogue_kernel<<<1, EPI_THREADS, 0, s>>>(c->d_part, c->d_evt_tile_begin, (int)c->evt.nrows, c->n_evt_tiles,
-                                              c->n_sel_tiles, (double)c->sel.ncols, c->d_blob, neff_dev, partial_dev);
+    epilogue_kernel<<<1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->d_blob,
+                                              neff_dev, partial_dev);
     CK(cudaGetLastError());
     return BUMP_OK;
 }
@@ -585,9 +571,9 @@ int bump_launches_per_eval(const bump_ctx* c) { return c ? 4 : 0; }
 int bump_plan_info(bump_ctx* c, int64_t* info8) {
     if (!info8) return fail(BUMP_E_INVALID, "null info");
     if (int r = ensure_ready(c)) return r;
-    info8[0] = c->ntiles;
-    info8[1] = c->n_evt_tiles;
-    info8[2] = c->n_sel_tiles;
+    info8[0] = c->work.n_groups;
+    info8[1] = c->work.gpw;
+    info8[2] = c->nrecords;
     info8[3] = c->grid;
     info8[4] = STREAM_THREADS;
     info8[5] = STREAM_SMEM_BYTES;

@@ -26,7 +26,7 @@ namespace bump {
 #endif
 constexpr int STREAM_THREADS = BUMP_STREAM_THREADS;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
-constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/ + STREAM_WARPS * (NACC + 2) * 8;
+constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/;
 constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
@@ -224,80 +224,112 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
 }
 
-// Block-wide merge of the per-thread accumulators, deterministic order; result written by threads 0..NACC+1.
-__device__ __forceinline__ void tile_reduce(ThreadAcc& A, double* red, double* __restrict__ out,
-                                            const double* __restrict__ expt) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Warp-wide merge of the per-lane accumulators (fixed shuffle tree: deterministic) -> one record.
+__device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
     double mx = A.m;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    __syncthreads();   // protects `red` against the previous tile's readers
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-#pragma unroll
-    for (int w = 1; w < STREAM_WARPS; ++w) mx = fmax(mx, red[w]);
     const double sc = (A.m == -INFINITY) ? 0.0 : exp(A.m - mx);
     A.a[0] *= sc;
     A.a[1] *= sc * sc;
 #pragma unroll
     for (int k = 2; k < NACC; ++k) A.a[k] *= sc;
-    double v[NACC + 1];
+    double nv = (double)A.nvalid;
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) v[k] = A.a[k];
-    v[NACC] = (double)A.nvalid;
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    double mine = 0.0;   // lane k keeps the k-th sum
 #pragma unroll
-    for (int k = 0; k <= NACC; ++k) {
+    for (int k = 0; k < NACC; ++k) {
+        double v = A.a[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == k) mine = v;
     }
-    __syncthreads();
-    double* r2 = red + STREAM_WARPS;   // [STREAM_WARPS][NACC+1]
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k <= NACC; ++k) r2[warp * (NACC + 1) + k] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x <= NACC) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < STREAM_WARPS; ++w) s += r2[w * (NACC + 1) + threadIdx.x];
-        out[1 + threadIdx.x] = s;   // [1..NACC] sums, [NACC+1] nvalid
-    }
-    if (threadIdx.x == 0) out[0] = mx;
+    if (lane < NACC) out[1 + lane] = mine;
+    if (lane == NACC) out[1 + NACC] = nv;
+    if (lane == 31) out[0] = mx;
 }
 
+// Persistent, warp-autonomous streaming kernel.  After the table blob has been staged into shared memory (TMA
+// bulk copy, one mbarrier) no warp ever synchronises with another: warp w walks its range of 64-sample groups
+// [w*gpw, (w+1)*gpw), lane l evaluating samples 2l and 2l+1 of each group (one 128-bit load per column), and
+// flushes a record whenever the event changes.
 template <bool WA>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
-stream_kernel(const Columns cols, const Tile* __restrict__ tiles, const int ntiles,
+stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_blob = reinterpret_cast<double*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + BLOB_BYTES);
-    double* red = reinterpret_cast<double*>(smem_raw + BLOB_BYTES + 16);
 
     stage_tables(s_blob, mbar, g_blob);
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const Tile T = tiles[tile];
-        const double* const* c = T.set ? cols.sel : cols.evt;
-        const double2* c_dl = reinterpret_cast<const double2*>(c[C_DL] + T.off);
-        const double2* c_m1 = reinterpret_cast<const double2*>(c[C_M1D] + T.off);
-        const double2* c_q = reinterpret_cast<const double2*>(c[C_Q] + T.off);
-        const double2* c_lm = reinterpret_cast<const double2*>(c[C_LM] + T.off);
-        const double2* c_lq = reinterpret_cast<const double2*>(c[C_LQ] + T.off);
-        const double2* c_l1q = reinterpret_cast<const double2*>(c[C_L1Q] + T.off);
-        const double2* c_lpd = reinterpret_cast<const double2*>(c[C_LPD] + T.off);
-        ThreadAcc A;
-        acc_init(A);
-        const int npairs = T.count >> 1;
-        for (int p = threadIdx.x; p < npairs; p += STREAM_THREADS) {
-            const double2 dl = __ldg(c_dl + p), m1 = __ldg(c_m1 + p), q = __ldg(c_q + p), lm = __ldg(c_lm + p),
-                          lq = __ldg(c_lq + p), l1q = __ldg(c_l1q + p), lpd = __ldg(c_lpd + p);
-            eval_sample<WA>(dl.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, A);
-            eval_sample<WA>(dl.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, A);
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
+    if (warp >= wk.nwarps) return;
+    const int64_t g0 = (int64_t)warp * wk.gpw;
+    const int64_t g1 = min(g0 + wk.gpw, wk.n_groups);
+    if (g0 >= g1) return;
+    const int64_t e_first = group_event(wk, g0);
+    double* rec = part + (size_t)rec_off[warp] * PART_STRIDE;
+
+    // position of group g0: event e, group-in-event k
+    int64_t e = e_first;
+    int64_t k = (e < wk.nobs) ? g0 - e * wk.g_evt : g0 - wk.n_evt_groups;
+    ThreadAcc A;
+    acc_init(A);
+    // first sample of group (ee, kk) in column 0, the column pitch of its set, and its number of sample pairs
+    auto locate = [&](const int64_t ee, const int64_t kk, const double*& p0, int64_t& pitch, int& pairs) {
+        const bool is_sel = ee >= wk.nobs;
+        const int64_t stride = is_sel ? wk.sel_stride : wk.evt_stride;
+        p0 = (is_sel ? cols.sel_base : cols.evt_base + ee * stride) + kk * GROUP;
+        pitch = is_sel ? cols.sel_pitch : cols.evt_pitch;
+        pairs = (int)min((int64_t)GROUP, stride - kk * GROUP) >> 1;
+    };
+    auto load = [&](const double* p0, const int64_t pitch, const int col) {
+        return __ldg(reinterpret_cast<const double2*>(p0 + col * pitch) + lane);
+    };
+    const double* p0;
+    int64_t pitch;
+    int pairs;
+    locate(e, k, p0, pitch, pairs);
+    const double2 SENT = make_double2(1.0, 1.0);
+    double2 dl = (lane < pairs) ? load(p0, pitch, C_DL) : SENT;
+    for (int64_t g = g0; g < g1; ++g) {
+        // ---- this group's remaining columns (d_L was fetched one group ahead)
+        const bool on = lane < pairs;
+        double2 m1 = SENT, q = SENT, lm = make_double2(0.0, 0.0), lq = lm, l1q = lm, lpd = lm;
+        if (on) {
+            m1 = load(p0, pitch, C_M1D);
+            q = load(p0, pitch, C_Q);
+            lm = load(p0, pitch, C_LM);
+            lq = load(p0, pitch, C_LQ);
+            l1q = load(p0, pitch, C_L1Q);
+            lpd = load(p0, pitch, C_LPD);
         }
-        tile_reduce(A, red, part + (size_t)tile * PART_STRIDE, s_blob + OFF_EXPT);
+        const double2 dl_cur = dl;
+        // ---- advance to the next group and prefetch its d_L (the first thing an evaluation needs)
+        int64_t e_next = e, k_next = k + 1;
+        const int64_t gcount = (e < wk.nobs) ? wk.g_evt : (wk.n_groups - wk.n_evt_groups);
+        if (k_next == gcount) {
+            k_next = 0;
+            e_next = e + 1;
+        }
+        const bool more = g + 1 < g1;
+        if (more) {
+            locate(e_next, k_next, p0, pitch, pairs);
+            dl = (lane < pairs) ? load(p0, pitch, C_DL) : SENT;
+        }
+        // ---- evaluate (inactive lanes carry the zero-weight sentinel: no divergence inside)
+        eval_sample<WA>(dl_cur.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, A);
+        eval_sample<WA>(dl_cur.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, A);
+        if (!more || e_next != e) {   // event complete (for this warp): one record
+            warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
+            acc_init(A);
+        }
+        e = e_next;
+        k = k_next;
     }
 }
 

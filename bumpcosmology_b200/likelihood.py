@@ -184,7 +184,7 @@ class Hyperlikelihood:
     def plan(self):
         info = (C.c_int64 * 8)()
         _lib.check(self.lib.bump_plan_info(self._ctx, info))
-        keys = ("tiles", "event_tiles", "injection_tiles", "grid", "threads", "smem_bytes", "padded_samples", "sms")
+        keys = ("groups", "groups_per_warp", "records", "grid", "threads", "smem_bytes", "padded_samples", "sms")
         return dict(zip(keys, [int(v) for v in info]))
 
     @property

@@ -125,7 +125,7 @@ int bump_time_evals(bump_ctx* ctx, const double* theta, int iters, float* total_
 /* Number of kernel launches one bump_eval performs (for bench.py's gpu_launches). */
 int bump_launches_per_eval(const bump_ctx* ctx);
 
-/* Execution plan of the streaming kernel: info8 = {tiles, event tiles, injection tiles, grid (CTAs), threads
+/* Execution plan of the streaming kernel: info8 = {64-sample groups, groups per warp, records, grid (CTAs), threads
  * per CTA, dynamic shared memory bytes, padded samples resident on this rank, SM count}. */
 int bump_plan_info(bump_ctx* ctx, int64_t* info8);
 
