@@ -14,7 +14,7 @@
 
 namespace bump {
 
-constexpr int EPI_THREADS = 512;
+constexpr int EPI_THREADS = 256;
 
 // Gradient of (logsumexp + theta-only constant) from softmax-weighted features phi (already normalised and, for
 // events, summed over n events).  g[15] in theta order; sc = scalar block of the table blob.
@@ -145,91 +145,158 @@ __device__ __forceinline__ size_t record_of(const Work& wk, const int* __restric
     return (size_t)rec_off[w] + (size_t)(e - group_event(wk, w * wk.gpw));
 }
 
-// One block.  part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt))
-// is covered by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
+// part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt)) is covered
+// by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
+//   blocks 0 .. nb_evt-1 : one thread per event -> logsumexp, Neff, normalised features; block sum -> slot[b]
+//   block  nb_evt        : the injection records -> slot[nb_evt]
+//   last block to finish : fixed-order sum of the slots -> this rank's partial; with `out_header` non-null
+//                          (single rank) it also finalizes, saving a launch.
+constexpr int EPI_SLOT = 24;
 __global__ void __launch_bounds__(EPI_THREADS)
 epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off, const Work wk, const double nsel,
-                const double* __restrict__ blob, double* __restrict__ neff_out, double* __restrict__ partial) {
+                const int lpe /* lanes per event: power of two <= 32 */, const double* __restrict__ blob,
+                double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
+                double* __restrict__ partial, double* __restrict__ out_header) {
     __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
     __shared__ double s_max;
+    __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int nobs = wk.nobs;
-    // ---- events
-    double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
+    const int epb = EPI_THREADS / lpe;   // events per block
+    const int nb_evt = (nobs + epb - 1) / epb;
+    double* slot = slots + (size_t)blockIdx.x * EPI_SLOT;
+    if ((int)blockIdx.x < nb_evt) {
+        // ---- events
+        double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
 #pragma unroll
-    for (int k = 0; k < NFEAT + 3; ++k) ev[k] = 0.0;
-    for (int e = tid; e < nobs; e += EPI_THREADS) {
+        for (int k = 0; k < NFEAT + 3; ++k) ev[k] = 0.0;
+        const int e = blockIdx.x * epb + tid / lpe;
+        const int sub = tid % lpe;
         double m = -INFINITY, a[NACC], nv = 0.0;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) a[k] = 0.0;
-        const int64_t w0 = (e * wk.g_evt) / wk.gpw, w1 = ((e + 1) * wk.g_evt - 1) / wk.gpw;
-        for (int64_t w = w0; w <= w1; ++w) {
-            const double* p = part + record_of(wk, rec_off, w, e) * PART_STRIDE;
+        if (e < nobs) {
+            const int64_t w0 = (e * wk.g_evt) / wk.gpw, w1 = ((e + 1) * wk.g_evt - 1) / wk.gpw;
+            for (int64_t w = w0 + sub; w <= w1; w += lpe) {
+                const double* p = part + record_of(wk, rec_off, w, e) * PART_STRIDE;
+                double b[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) b[k] = p[1 + k];
+                lse_merge(m, a, p[0], b);
+                nv += p[1 + NACC];
+            }
+        }
+        for (int o = lpe >> 1; o > 0; o >>= 1) {   // fixed butterfly over the event's lanes: deterministic
             double b[NACC];
+            const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) b[k] = p[1 + k];
-            lse_merge(m, a, p[0], b);
-            nv += p[1 + NACC];
+            for (int k = 0; k < NACC; ++k) b[k] = __shfl_xor_sync(0xffffffffu, a[k], o);
+            nv += __shfl_xor_sync(0xffffffffu, nv, o);
+            // both partners must end with identical bits: merge in (lower lane, upper lane) order
+            if (sub & o) {
+                double mm = m2, aa[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) aa[k] = b[k];
+                lse_merge(mm, aa, m, a);
+                m = mm;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) a[k] = aa[k];
+            } else {
+                lse_merge(m, a, m2, b);
+            }
         }
-        if (m == -INFINITY || !(a[0] > 0.0)) {   // no finite-weight sample: logsumexp = -inf (reference: same)
-            ev[2] += 1.0;
-            neff_out[e] = NAN;
-            continue;
+        if (e < nobs && sub == 0) {
+            if (m == -INFINITY || !(a[0] > 0.0)) {   // no finite-weight sample: logsumexp = -inf (reference: same)
+                ev[2] = 1.0;
+                neff_out[e] = NAN;
+            } else {
+                const double iS = 1.0 / a[0];
+                ev[0] = m + log(a[0]);
+                ev[1] = nv;
+                neff_out[e] = a[0] * a[0] / a[1];   // exp(2 lse(w) - lse(2w)), :401
+#pragma unroll
+                for (int k = 0; k < NFEAT; ++k) ev[3 + k] = a[2 + k] * iS;
+            }
         }
-        const double iS = 1.0 / a[0];
-        ev[0] += m + log(a[0]);
-        ev[1] += nv;
-        neff_out[e] = a[0] * a[0] / a[1];   // exp(2 lse(w) - lse(2w)), :401
+        epi_block_sum<NFEAT + 3>(ev, red);
+        if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NFEAT; ++k) ev[3 + k] += a[2 + k] * iS;
+            for (int k = 0; k < NFEAT + 3; ++k) slot[k] = ev[k];
+        }
+    } else {
+        // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps owning its groups
+        const bool has_sel = wk.n_groups > wk.n_evt_groups;
+        const int64_t ws0 = has_sel ? wk.n_evt_groups / wk.gpw : 0;
+        const int64_t ws1 = has_sel ? (wk.n_groups - 1) / wk.gpw : -1;
+        double mx = -INFINITY;
+        for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS)
+            mx = fmax(mx, part[record_of(wk, rec_off, w, nobs) * PART_STRIDE]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            double m = red[0];
+            for (int w = 1; w < EPI_THREADS / 32; ++w) m = fmax(m, red[w]);
+            s_max = m;
+        }
+        __syncthreads();
+        mx = s_max;
+        double sv[NACC + 1];
+#pragma unroll
+        for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
+        for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
+            const double* p = part + record_of(wk, rec_off, w, nobs) * PART_STRIDE;
+            if (p[0] == -INFINITY) continue;
+            const double s = exp(p[0] - mx);
+            sv[0] += p[1] * s;
+            sv[1] += p[2] * (s * s);
+#pragma unroll
+            for (int k = 2; k < NACC; ++k) sv[k] += p[1 + k] * s;
+            sv[NACC] += p[1 + NACC];
+        }
+        epi_block_sum<NACC + 1>(sv, red);
+        if (tid == 0) {
+            slot[0] = mx;
+#pragma unroll
+            for (int k = 0; k <= NACC; ++k) slot[1 + k] = sv[k];
+        }
     }
-    epi_block_sum<NFEAT + 3>(ev, red);
-    // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps that own its groups
-    const bool has_sel = wk.n_groups > wk.n_evt_groups;
-    const int64_t ws0 = has_sel ? wk.n_evt_groups / wk.gpw : 0;
-    const int64_t ws1 = has_sel ? (wk.n_groups - 1) / wk.gpw : -1;
-    double mx = -INFINITY;
-    for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS)
-        mx = fmax(mx, part[record_of(wk, rec_off, w, nobs) * PART_STRIDE]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // ---- last block: fixed-order sum of the slots
+    __threadfence();
     __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    if (tid == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (tid == 0) {
-        double m = red[0];
-        for (int w = 1; w < EPI_THREADS / 32; ++w) m = fmax(m, red[w]);
-        s_max = m;
+    if (!is_last) return;
+    __threadfence();
+    if (tid < NFEAT + 3) {
+        double s = 0.0;
+        for (int b = 0; b < nb_evt; ++b) s += __ldcg(slots + (size_t)b * EPI_SLOT + tid);
+        red[tid] = s;
     }
     __syncthreads();
-    mx = s_max;
-    double sv[NACC + 1];
-#pragma unroll
-    for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
-    for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
-        const double* p = part + record_of(wk, rec_off, w, nobs) * PART_STRIDE;
-        if (p[0] == -INFINITY) continue;
-        const double s = exp(p[0] - mx);
-        sv[0] += p[1] * s;
-        sv[1] += p[2] * (s * s);
-#pragma unroll
-        for (int k = 2; k < NACC; ++k) sv[k] += p[1 + k] * s;
-        sv[NACC] += p[1 + NACC];
+    if (tid < P_SCAL0) {
+        const double* ss = slots + (size_t)nb_evt * EPI_SLOT;
+        double v = 0.0;
+        if (tid == P_LLSUM) v = red[0];
+        else if (tid == P_NOBS) v = (double)nobs;
+        else if (tid >= P_FSUM0 && tid < P_FSUM0 + NFEAT) v = red[3 + tid - P_FSUM0];
+        else if (tid == P_NVALID_EVT) v = red[1];
+        else if (tid == P_NDEAD_EVT) v = red[2];
+        else if (tid == P_SEL_M) v = __ldcg(ss);
+        else if (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) v = __ldcg(ss + 1 + tid - P_SEL_ACC0);
+        else if (tid == P_NVALID_SEL) v = __ldcg(ss + 1 + NACC);
+        else if (tid == P_NSEL) v = nsel;
+        partial[tid] = v;
+    } else if (tid < P_SCAL0 + NSCAL) {
+        partial[tid] = blob[OFF_SCAL + tid - P_SCAL0];
     }
-    epi_block_sum<NACC + 1>(sv, red);
-    if (tid == 0) {
-        for (int k = 0; k < P_SCAL0; ++k) partial[k] = 0.0;
-        partial[P_LLSUM] = ev[0];
-        partial[P_NOBS] = (double)nobs;
-        partial[P_NVALID_EVT] = ev[1];
-        partial[P_NDEAD_EVT] = ev[2];
-        for (int k = 0; k < NFEAT; ++k) partial[P_FSUM0 + k] = ev[3 + k];
-        partial[P_SEL_M] = mx;
-        for (int k = 0; k < NACC; ++k) partial[P_SEL_ACC0 + k] = sv[k];
-        partial[P_NVALID_SEL] = sv[NACC];
-        partial[P_NSEL] = nsel;
+    if (tid == 0) *ticket = 0u;
+    if (out_header) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) finalize_merge(partial, 1, out_header);
     }
-    if (tid < NSCAL) partial[P_SCAL0 + tid] = blob[OFF_SCAL + tid];
 }
 
 }  // namespace bump

@@ -1,11 +1,11 @@
 // libbump_b200.so — C ABI (include/bump.h) over the sm_100a kernels.  CUDA runtime only; no torch, no CPU fallback.
 //
 // One evaluation = 4 launches replayed from a CUDA graph:
-//   prologue_kernel  (bump_tables.cuh)   theta -> tables + tangents + scalars           (F1-F3 of SURVEY.md 2.2)
-//   stream_kernel    (bump_stream.cuh)   one pass over the SoA columns -> per-tile sums (F4-F7 + reverse pass)
-//   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial
-//   [ncclAllGather of the 1 KiB partial when a communicator is attached]
-//   finalize_kernel  (bump_epilogue.cuh) rank-ordered merge, constants, chain rule -> result header
+//   tables_kernel    (bump_tables.cuh)   theta -> PISN and cosmology tables + tangents  (F1-F2 of SURVEY.md 2.2)
+//   records_kernel   (bump_tables.cuh)   packed per-bin records, d_L bucket table, scalars (F3)
+//   stream_kernel    (bump_stream.cuh)   one pass over the SoA columns -> per-warp records (F4-F7 + reverse pass)
+//   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial, and (single rank) the result
+//   [multi-rank: ncclAllGather of the 1 KiB partial, then finalize_kernel: rank-ordered merge -> result header]
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
@@ -163,9 +163,10 @@ struct bump_ctx {
     // plan
     bool plan_dirty = true;
     Work work{};
-    int nrecords = 0, grid = 0, sm_count = 0;
+    int nrecords = 0, grid = 0, sm_count = 0, lpe = 1;
     int* d_rec_off = nullptr;
     double* d_part = nullptr;
+    double* d_slots = nullptr;
     // workspaces
     double *d_theta = nullptr, *d_aux = nullptr, *d_blob = nullptr, *d_partial = nullptr, *d_gather = nullptr,
            *d_out = nullptr;
@@ -190,6 +191,7 @@ void free_plan(bump_ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
     cudaFree(c->d_rec_off), c->d_rec_off = nullptr;
     cudaFree(c->d_part), c->d_part = nullptr;
+    cudaFree(c->d_slots), c->d_slots = nullptr;
     cudaFree(c->d_out), c->d_out = nullptr;
     if (c->h_out) cudaFreeHost(c->h_out), c->h_out = nullptr;
 }
@@ -264,9 +266,15 @@ int build_plan(bump_ctx* c) {
         rec_off[i + 1] = rec_off[i] + n;
     }
     c->nrecords = rec_off[w.nwarps];
+    // epilogue: lanes per event = records per event rounded up to a power of two (<= 32)
+    const int64_t rpe = (w.g_evt + w.gpw - 1) / w.gpw + 1;
+    c->lpe = 1;
+    while (c->lpe < 32 && c->lpe < rpe) c->lpe *= 2;
     c->out_len = OUT_HEADER + c->evt.nrows;
     CK(cudaMalloc(&c->d_rec_off, sizeof(int) * rec_off.size()));
     CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max(1, c->nrecords)));
+    const int epb = EPI_THREADS / c->lpe;
+    CK(cudaMalloc(&c->d_slots, sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + 1)));
     CK(cudaMalloc(&c->d_out, sizeof(double) * c->out_len));
     CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
     CK(cudaMemcpy(c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size(), cudaMemcpyHostToDevice));
@@ -293,8 +301,9 @@ EvalConsts consts_of(const bump_ctx* c) {
 
 // The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
-                   cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr) {
-    prologue_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket, consts_of(c));
+                   cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr) {
+    tables_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_ticket + 2, c->use_wa ? 1 : 0);
+    records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0) {
         if (c->use_wa)
@@ -305,22 +314,25 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                                                                                     c->d_rec_off, c->d_blob, c->d_part);
     }
     if (k1) cudaEventRecord(k1, s);
-    epilogue_kernel<<<1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->d_blob,
-                                              neff_dev, partial_dev);
+    const int epb = EPI_THREADS / c->lpe;
+    const int nb_evt = (c->work.nobs + epb - 1) / epb;
+    epilogue_kernel<<<nb_evt + 1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->lpe,
+                                                       c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
+                                                       fused_out);
     CK(cudaGetLastError());
     return BUMP_OK;
 }
 
 int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStream_t s, cudaEvent_t k0 = nullptr,
                 cudaEvent_t k1 = nullptr) {
-    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1)) return r;
-    const double* merged = c->d_partial;
+    // single rank: the epilogue's last block finalizes in place (3 launches per evaluation)
+    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev))
+        return r;
     if (c->comm) {
         NCK(g_nccl.AllGather(c->d_partial, c->d_gather, PARTIAL_LEN, NCCL_FLOAT64, c->comm, s));
-        merged = c->d_gather;
+        finalize_kernel<<<1, 32, 0, s>>>(c->d_gather, c->nranks, out_dev);
+        CK(cudaGetLastError());
     }
-    finalize_kernel<<<1, 32, 0, s>>>(merged, c->nranks, out_dev);
-    CK(cudaGetLastError());
     return BUMP_OK;
 }
 
@@ -393,8 +405,8 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaMalloc(&c->d_blob, BLOB_BYTES));
     CK(cudaMemset(c->d_blob, 0, BLOB_BYTES));
     CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
-    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int)));
-    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));   // [0] prologue ticket, [1] epilogue ticket, [2] bad flag
+    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -566,7 +578,7 @@ int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms
     return BUMP_OK;
 }
 
-int bump_launches_per_eval(const bump_ctx* c) { return c ? 4 : 0; }
+int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 5 : 4) : 0; }
 
 int bump_plan_info(bump_ctx* c, int64_t* info8) {
     if (!info8) return fail(BUMP_E_INVALID, "null info");

@@ -1,9 +1,5 @@
-// Prologue: theta-dependent tables with forward-mode tangents, one launch.
-//
-//   blocks 0..NM-1 : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
-//   block  NM      : flat wCDM distance tables        (intensity_models.py:229-235 + utils.py:3-8 cumtrapz)
-//   last block to finish (atomic ticket): scalars (intensity_models.py:134-138,167-168) and the packed
-//   per-bin records the streaming kernel bulk-copies into shared memory.
+// Prologue: theta-dependent tables with forward-mode tangents (tables_kernel), then the packed per-bin records
+// and scalars the streaming kernel bulk-copies into shared memory (records_kernel).
 #pragma once
 #include "bump_dual.cuh"
 #include "bump_layout.cuh"
@@ -201,8 +197,10 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
 }
 
 // ---------------------------------------------------------------- scalars (Dual<7>: a, b, c, mpisn, mbhmax, sigma, fpl)
-__device__ void build_scalars(const double* th, const double* aux_, const EvalConsts ec, double* scal) {
-    const CgView aux{aux_};   // written by other blocks of this launch: read through L2 (ld.global.cg)
+// gtab = [6][NM] copy of aux[AUX_G ...] (shared memory); aux_ = the global workspace (for two d_L knots)
+__device__ void build_scalars(const double* th, const double* aux_, const double* gtab, const EvalConsts ec,
+                              double* scal) {
+    const CgView aux{aux_};
     typedef Dual<7> D;
     const int map5[5] = {0, 1, 3, 4, 5};   // (a, b, mpisn, mbhmax, sigma) -> slots of Dual<7>
     D c = D::var(th[T_C], 2), M = D::var(th[T_MBHMAX], 4), sg = D::var(th[T_SIGMA], 5), fpl = D::var(th[T_FPL], 6);
@@ -212,9 +210,9 @@ __device__ void build_scalars(const double* th, const double* aux_, const EvalCo
         return (k == NM - 1) ? top : (MIN_BH_MASS * (1.0 - s) + top * s);
     };
     auto Gk = [&](int k) -> D {
-        D g(aux[AUX_G + k]);
+        D g(gtab[k]);
 #pragma unroll
-        for (int q = 0; q < 5; ++q) g.d[map5[q]] = aux[AUX_G + (q + 1) * NM + k];
+        for (int q = 0; q < 5; ++q) g.d[map5[q]] = gtab[(q + 1) * NM + k];
         return g;
     };
     // jnp.interp(m, mbh_grid, log_dN_grid), differentiable in m, the knots and the values (:110-111)
@@ -281,83 +279,106 @@ __device__ void build_scalars(const double* th, const double* aux_, const EvalCo
     scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
 
-__device__ void build_records(const double* aux_, int use_wa, double* blob) {
-    const CgView aux{aux_};
+// ---------------------------------------------------------------- kernel 1: raw tables with tangents
+//   blocks 0..NM-1 : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
+//   block  NM      : flat wCDM distance tables        (intensity_models.py:229-235 + utils.py:3-8 cumtrapz)
+__global__ void __launch_bounds__(PRO_THREADS)
+tables_kernel(const double* __restrict__ theta, double* __restrict__ aux, unsigned int* __restrict__ flags,
+              const int use_wa) {
+    __shared__ double sm[9 * NM + 64];
+    __shared__ double th[NTHETA_MAX];
+    if (threadIdx.x < NTHETA_MAX) th[threadIdx.x] = (threadIdx.x < NTHETA || use_wa) ? theta[threadIdx.x] : 0.0;
+    __syncthreads();
+    if (blockIdx.x < NM) pisn_row(th, blockIdx.x, aux, sm);
+    else cosmology_tables(th, use_wa, aux, sm);
+    // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
+    int bad = 0;
+    __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
+    if (blockIdx.x < NM) {
+        if (threadIdx.x < 6) bad = !isfinite(__ldcg(aux + AUX_G + threadIdx.x * NM + blockIdx.x));
+    } else {
+        for (int q = 0; q < NZ / PRO_THREADS; ++q) {
+            const int k = threadIdx.x * (NZ / PRO_THREADS) + q;
+            for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));
+        }
+        if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1u);
+}
+
+// ---------------------------------------------------------------- kernel 2: packed records + scalars
+// One item per thread: NZ cosmology bins, NM mass bins, SRCH_N d_L buckets, NEXPT exp-table entries; the extra
+// last block derives the scalars (intensity_models.py:134-138,167-168) from a shared-memory copy of the PISN table.
+constexpr int REC_ITEMS = NZ + NM + SRCH_N + NEXPT;
+constexpr int REC_BLOCKS = (REC_ITEMS + PRO_THREADS - 1) / PRO_THREADS;   // + 1 block for the scalars
+
+__global__ void __launch_bounds__(PRO_THREADS)
+records_kernel(const double* __restrict__ theta, const double* __restrict__ aux, double* __restrict__ blob,
+               unsigned int* __restrict__ flags, const EvalConsts ec) {
+    __shared__ double sm[6 * NM];
+    if (blockIdx.x == REC_BLOCKS) {
+        for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) sm[k] = aux[AUX_G + k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double th[NTHETA_MAX];
+            for (int k = 0; k < NTHETA_MAX; ++k) th[k] = (k < NTHETA || ec.use_wa) ? theta[k] : 0.0;
+            build_scalars(th, aux, sm, ec, blob + OFF_SCAL);
+            blob[OFF_SCAL + S_BAD] = (*flags != 0u) ? 1.0 : 0.0;
+            *flags = 0u;
+        }
+        return;
+    }
     double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
     double* ctan = blob + OFF_CTAN;
-    double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
-    unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
-    const CgView dl = aux + AUX_DL;
-    for (int b = threadIdx.x; b < NZ; b += blockDim.x) {
-        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
+    int item = blockIdx.x * PRO_THREADS + threadIdx.x;
+    const bool need_dl = (blockIdx.x + 1) * PRO_THREADS > NZ + NM;   // this block holds d_L bucket items
+    if (need_dl) {
+        for (int k = threadIdx.x; k < NZ; k += PRO_THREADS) sm[k] = aux[AUX_DL + k];
+        __syncthreads();
+    }
+    if (item < NZ) {
+        const int b = item, b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
+        const double* dl = aux + AUX_DL;
+        const double* dvc = aux + AUX_DVC;
+        const double* ddl = aux + AUX_DDL;
         cos[CR_DL * NZ + b] = make_double2(dl[b0], 1.0 / (dl[b1] - dl[b0]));
-        const CgView dvc = aux + AUX_DVC;
         cos[CR_DVC * NZ + b] = make_double2(dvc[b0], dvc[b1] - dvc[b0]);
-        const CgView ddl = aux + AUX_DDL;
         cos[CR_DDL * NZ + b] = make_double2(ddl[b0], ddl[b1] - ddl[b0]);
-        const double lz = b0 * ZSTEP;
-        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), lz);
+        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), b0 * ZSTEP);
         // tangent tables (knot values): aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan
         const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
 #pragma unroll
         for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
+        return;
     }
-    for (int b = threadIdx.x; b < NM; b += blockDim.x) {
-        const int b0 = min(b, NM - 2), b1 = b0 + 1;
+    item -= NZ;
+    if (item < NM) {
+        double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
+        const int b0 = min(item, NM - 2), b1 = b0 + 1;
 #pragma unroll
         for (int r = 0; r < NMREC; ++r) {
-            const CgView g = aux + (AUX_G + r * NM);
-            mass[r * NM + b] = make_double2(g[b0], g[b1] - g[b0]);
+            const double* g = aux + AUX_G + r * NM;
+            mass[r * NM + item] = make_double2(g[b0], g[b1] - g[b0]);
         }
+        return;
     }
-    // bucket table for the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j
-    for (int j = threadIdx.x; j < SRCH_N; j += blockDim.x) {
-        const int key = j + (SRCH_EXP_LO << SRCH_MBITS);
+    item -= NM;
+    if (item < SRCH_N) {
+        // bucket table for the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j
+        unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
+        const int key = item + (SRCH_EXP_LO << SRCH_MBITS);
         const double x0 = __hiloint2double(key << (20 - SRCH_MBITS), 0);   // smallest double of the bucket
         int pos = 0;                                                        // #{k < NZ-1 : dl_k <= x0}
-#pragma unroll 1
+#pragma unroll
         for (int step = NZ / 2; step >= 1; step >>= 1) {
-            if (dl[pos + step - 1] <= x0) pos += step;
+            if (sm[pos + step - 1] <= x0) pos += step;
         }
         const int b = min(max(pos, 1) - 1, NZ - 2);
-        srch[j] = (unsigned short)(j == 0 ? 0 : b);
+        srch[item] = (unsigned short)(item == 0 ? 0 : b);
+        return;
     }
-}
-
-__global__ void __launch_bounds__(PRO_THREADS)
-prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
-                unsigned int* __restrict__ ticket, EvalConsts ec) {
-    __shared__ double sm[9 * NM + 64];
-    __shared__ bool is_last;
-    __shared__ double th[NTHETA_MAX];
-    if (threadIdx.x < NTHETA_MAX) th[threadIdx.x] = (threadIdx.x < NTHETA || ec.use_wa) ? theta[threadIdx.x] : 0.0;
-    __syncthreads();
-    if (blockIdx.x < NM) pisn_row(th, blockIdx.x, aux, sm);
-    else cosmology_tables(th, ec.use_wa, aux, sm);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    build_records(aux, ec.use_wa, blob);
-    if (threadIdx.x < NEXPT) blob[OFF_EXPT + threadIdx.x] = exp2((double)threadIdx.x / NEXPT);
-    // non-finite theta or tables (theta outside the prior support): flag it, finalize returns NaN
-    int bad = 0;
-    {
-        const CgView a{aux};
-        for (int i = threadIdx.x; i < AUX_DOUBLES; i += blockDim.x) bad |= !isfinite(a[i]);
-        if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
-    }
-    bad = __syncthreads_or(bad);
-    if (threadIdx.x == 0) {
-        build_scalars(th, aux, ec, blob + OFF_SCAL);
-        blob[OFF_SCAL + S_BAD] = bad ? 1.0 : 0.0;
-        *ticket = 0u;
-    }
+    item -= SRCH_N;
+    if (item < NEXPT) blob[OFF_EXPT + item] = exp2((double)item / NEXPT);
 }
 
 }  // namespace bump

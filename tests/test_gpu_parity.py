@@ -177,3 +177,32 @@ def test_partials_merge_equals_single_rank(hl):
     assert _close(m["dlog_mu_sel"], r.dlog_mu_sel, rtol=1e-11)
     assert _close(np.concatenate(neffs), r.neff, rtol=1e-12)
     full.close()
+
+
+def test_out_of_support_theta_gives_nan_not_error(hl):
+    """mbhmax < mpisn (sqrt of a negative number in largest_mco) and a NaN parameter: the reference yields NaN,
+    NUTS treats it as a divergent step; the library must not raise, and must recover on the next call."""
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
+    cat = make_catalog("tiny")
+    like = hl(*cat.as_args())
+    good = like(THETA_DEFAULT)
+    bad = THETA_DEFAULT.copy()
+    bad[7] = bad[6] - 1.0
+    r = like(bad)
+    assert np.isnan(r.loglike) and np.all(np.isnan(r.dloglike))
+    bad = THETA_DEFAULT.copy()
+    bad[0] = np.nan
+    assert np.isnan(like(bad).log_mu_sel)
+    again = like(THETA_DEFAULT)
+    assert again.loglike == good.loglike and np.array_equal(again.dloglike, good.dloglike)
+    like.close()
+
+
+def test_repeat_evaluations_are_bitwise_identical(hl):
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
+    cat = make_catalog("small")
+    like = hl(*cat.as_args())
+    a, b = like(THETA_DEFAULT), like(THETA_DEFAULT)
+    assert a.loglike == b.loglike and a.log_mu_sel == b.log_mu_sel
+    assert np.array_equal(a.dloglike, b.dloglike) and np.array_equal(a.neff, b.neff)
+    like.close()
