@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference's model interface for the hot path.
+
+`pop_cosmo_model(m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw)` keeps the positional
+signature of /root/reference/src/scripts/intensity_models.py:357 and returns a `PopCosmoModel`: the catalog is
+uploaded to HBM once, and every call with sample-site values yields the numpyro-visible names of the reference
+model — factors `loglike`, `selfactor` (:383, :390), deterministics `mbhmax`, `fpl`, `kappa`, `neff_sel`, `R`,
+`neff`, `mdNdmdVdt_fixed_qz`, `dNdqdVdt_fixed_mz`, `dNdVdt_fixed_mq`, `hz` (:288-301, :394-406) — plus what JAX autodiff
+gives numpyro implicitly: the gradient of the factors with respect to the 14 sample sites.
+
+The likelihood and its gradient come from the CUDA library (no CPU fallback).  Only the 15-scalar prior /
+transform arithmetic (priors.py) and the output-only 128-point diagnostic curves are computed on the host.
+"""
+import math
+
+import numpy as np
+
+from . import priors
+from .likelihood import Hyperlikelihood, ShardedHyperlikelihood
+
+# intensity_models.py:275-279
+coords = {
+    "m_grid": np.exp(np.linspace(np.log(5), np.log(150), 128)),
+    "q_grid": np.linspace(0, 1, 129)[1:],
+    "z_grid": np.expm1(np.linspace(np.log1p(0), np.log1p(3), 128)),
+}
+MREF, QREF, ZREF = 30.0, 1.0, 0.0       # :129, :191-193
+SAMPLE_SITES = priors.SITE_NAMES           # 15 sites incl. R_unit
+LIKELIHOOD_SITES = priors.LIKELIHOOD_SITES
+
+
+class PopCosmoModel:
+    """The reference model bound to its data (what numpyro holds after `mcmc.run(key, *data)`)."""
+
+    def __init__(self, m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, device=0,
+                 distributed=False, exchange="torch"):
+        data = (m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw)
+        if distributed:
+            self.like = ShardedHyperlikelihood(data, device=device, exchange=exchange)
+            self._local = self.like.local
+        else:
+            self.like = self._local = Hyperlikelihood(*data, device=device)
+        self.n_evals = 0
+
+    # ---- site handling
+    @staticmethod
+    def _site_vector(sites):
+        if isinstance(sites, dict):
+            return np.array([float(sites.get(k, 0.0)) for k in SAMPLE_SITES])
+        x = np.asarray(sites, dtype=np.float64).ravel()
+        if x.shape[0] == 14:
+            x = np.concatenate([x, [0.0]])
+        if x.shape[0] != 15:
+            raise ValueError(f"expected the 15 sample sites {SAMPLE_SITES} (or the first 14)")
+        return x
+
+    def evaluate(self, sites, diagnostics=False):
+        """One model evaluation at the given sample-site values (dict or vector in SAMPLE_SITES order)."""
+        x = self._site_vector(sites)
+        theta = priors.theta_from_sites(x)
+        r = self.like(theta)
+        self.n_evals += 1
+        nobs = r.nobs
+        g_ll = priors.grad_sites_from_theta(r.dloglike, theta)
+        g_mu = priors.grad_sites_from_theta(r.dlog_mu_sel, theta)
+        mu_sel = math.exp(r.log_mu_sel) if math.isfinite(r.log_mu_sel) else float("nan")
+        out = {
+            "loglike": r.loglike, "selfactor": -nobs * r.log_mu_sel,                       # factors :383, :390
+            "mbhmax": theta[7], "fpl": theta[9], "kappa": theta[12],                        # :288, :294, :301
+            "log_mu_sel": r.log_mu_sel, "neff_sel": r.neff_sel, "neff": r.neff,             # :389, :394, :401
+            "R": nobs / mu_sel + math.sqrt(nobs) / mu_sel * x[14],                          # :399
+            "dloglike_dsite": g_ll, "dselfactor_dsite": -nobs * g_mu,
+            "nobs": nobs, "theta": theta,
+        }
+        if diagnostics:
+            out.update(self.diagnostics(theta, out["R"]))
+        return out
+
+    __call__ = evaluate
+
+    # ---- potential energy in unconstrained space, as numpyro's NUTS sees the model
+    def potential(self, u):
+        """U(u) = -[log prior(x(u)) + log|dx/du| + loglike + selfactor] and dU/du (15-dim, incl. R_unit)."""
+        x, dx, lj, dlj = priors.constrain(u)
+        lp, glp = priors.log_prior(x)
+        ev = self.evaluate(x)
+        logl = ev["loglike"] + ev["selfactor"]
+        if not (math.isfinite(logl) and math.isfinite(lp)):
+            return math.inf, np.zeros(priors.NSITES), ev
+        g = glp.copy()
+        g[:14] += ev["dloglike_dsite"] + ev["dselfactor_dsite"]
+        return -(lp + lj + logl), -(g * dx + dlj), ev
+
+    # ---- output-only curves (:403-406) from the tables the device built for this theta
+    def diagnostics(self, theta, R):
+        t = self._local.tables()
+        sc = t["scalars"]
+        log_norm, rate_log_norm, lpn = sc[18], sc[19], sc[6]
+        h, Om, w, c, mbhmax, sigma, beta, lam, kappa, zp = (theta[0], theta[1], theta[2], theta[5], theta[7],
+                                                             theta[8], theta[10], theta[11], theta[12], theta[13])
+        mbh_grid = np.linspace(3.0, mbhmax + 7 * sigma, 256)
+        G = t["log_dN_grid"]
+
+        def log_dndm(m):   # LogDNDM.__call__ :140-151
+            m = np.asarray(m, dtype=np.float64)
+            with np.errstate(divide="ignore", over="ignore"):
+                ld = np.interp(m, mbh_grid, G)
+                ld = np.where((m <= mbh_grid[0]) | (m >= mbh_grid[-1]), -np.inf, ld)
+                turn = math.log(2) - np.log1p(np.exp(-(m - mbhmax) / (0.05 * mbhmax)))
+                ld = np.logaddexp(ld, -c * np.log(m / mbhmax) + lpn + turn)
+                ld = np.where(m < 5.0, -np.inf, ld)
+            return ld + log_norm
+
+        def log_dndv(z):   # LogDNDV.__call__ :170-173
+            z = np.asarray(z, dtype=np.float64)
+            return lam * np.log1p(z) - np.log1p(((1 + z) / (1 + zp)) ** kappa) + rate_log_norm
+
+        def log_dN(m1, q, z):   # LogDNDMDQDV.__call__ :202-210
+            m1, q, z = np.broadcast_arrays(np.asarray(m1, float), np.asarray(q, float), np.asarray(z, float))
+            m2 = q * m1
+            with np.errstate(divide="ignore"):
+                return (log_dndm(m1) + log_dndm(m2) + beta * np.log((m1 + m2) / (MREF * (1 + QREF))) + np.log(m1)
+                        + log_dndv(z))
+
+        zg = coords["z_grid"]
+        opz = 1 + zg
+        return {
+            "mdNdmdVdt_fixed_qz": coords["m_grid"] * R * np.exp(log_dN(coords["m_grid"], QREF, ZREF)),
+            "dNdqdVdt_fixed_mz": MREF * R * np.exp(log_dN(MREF, coords["q_grid"], ZREF)),
+            "dNdVdt_fixed_mq": MREF * R * np.exp(log_dN(MREF, QREF, zg)),
+            "hz": h * np.sqrt(Om * opz ** 3 + (1 - Om) * opz ** (3 * (1 + w))),      # :253-256
+        }
+
+    def close(self):
+        self._local.close()
+
+
+def pop_cosmo_model(m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, **kwargs):
+    """Same positional signature as the reference model (intensity_models.py:357); returns the bound model."""
+    return PopCosmoModel(m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, **kwargs)

@@ -206,3 +206,26 @@ def test_repeat_evaluations_are_bitwise_identical(hl):
     assert a.loglike == b.loglike and a.log_mu_sel == b.log_mu_sel
     assert np.array_equal(a.dloglike, b.dloglike) and np.array_equal(a.neff, b.neff)
     like.close()
+
+
+def test_host_model_mirror_matches_reference_sites_and_curves(golden_dir):
+    """bumpcosmology_b200.intensity_models.pop_cosmo_model: same signature and site names as the reference;
+    factors, deterministics, site gradients and the 128-point diagnostic curves against the goldens."""
+    from bumpcosmology_b200 import intensity_models as im
+    g = _load(golden_dir, "small")
+    model = im.pop_cosmo_model(*_data(g))
+    names = [str(s) for s in g["site_names"]]
+    assert tuple(names) == im.LIKELIHOOD_SITES
+    for k, th in enumerate(g["thetas"]):
+        sites = dict(h=th[0], Om=th[1], w=th[2], a=th[3], b=th[4], c=th[5], mpisn=th[6], dmbhmax=th[7] - th[6],
+                     sigma=th[8], beta=th[10], log_fpl=np.log(th[9]), lam=th[11], dkappa=th[12] - th[11], zp=th[13],
+                     R_unit=0.25)
+        r = model(sites, diagnostics=True)
+        assert _close(r["loglike"], g["ref_loglike"][k]) and _close(r["selfactor"], g["ref_selfactor"][k])
+        assert _close(r["R"], g["ref_R"][k]) and _close(r["neff_sel"], g["ref_neff_sel"][k])
+        scale = max(1.0, float(np.max(np.abs(g["ref_dloglike_dsite"][k]))))
+        assert _close(r["dloglike_dsite"], g["ref_dloglike_dsite"][k], floor=scale)
+        for name in ("mdNdmdVdt_fixed_qz", "dNdqdVdt_fixed_mz", "dNdVdt_fixed_mq", "hz"):
+            ref = g["ref_" + name][k]
+            assert _close(r[name], ref, rtol=1e-9, floor=max(1e-300, float(np.max(np.abs(ref))) * 1e-6)), (k, name)
+    model.close()
