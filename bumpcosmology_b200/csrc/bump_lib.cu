@@ -118,7 +118,8 @@ __global__ void locality_keys_kernel(const double* __restrict__ m1d, const doubl
 __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const double* __restrict__ q,
                                        const double* __restrict__ dl, const double* __restrict__ pd,
                                        const unsigned int* __restrict__ perm, const int64_t nrows,
-                                       const int64_t ncols, const int64_t stride, ColumnPtrs out) {
+                                       const int64_t ncols, const int64_t stride, ColumnPtrs out,
+                                       unsigned int* __restrict__ bad) {
     const int64_t total = nrows * stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / stride, c = i - r * stride;
@@ -126,6 +127,10 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
             int64_t s = r * ncols + c;
             if (perm) s = perm[s];
             const double vm = m1d[s], vq = q[s];
+            // the kernels assume finite, positive inputs (the reference would produce NaN / -inf weights)
+            if (!(vm > 0.0 && vq > 0.0 && dl[s] > 0.0 && pd[s] > 0.0 && isfinite(vm) && isfinite(vq) &&
+                  isfinite(dl[s]) && isfinite(pd[s])))
+                atomicOr(bad, 1u);
             out.c[C_DL][i] = dl[s];
             out.c[C_M1D][i] = vm;
             out.c[C_Q][i] = vq;
@@ -209,7 +214,7 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     c->plan_dirty = true;
     const int64_t n = nrows * ncols, npad = nrows * ds.stride;
     if (npad == 0) return BUMP_OK;
-    CK(cudaMalloc(&ds.base, sizeof(double) * NCOL * npad));
+    CK(cudaMalloc(&ds.base, sizeof(double) * (NCOL * npad + 2 * GROUP)));   // slack: the kernel prefetches one group ahead
     double* raw = nullptr;
     CK(cudaMalloc(&raw, sizeof(double) * 4 * n));
     const double* src[4] = {m1d, q, dl, pd};
@@ -234,12 +239,20 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
         CK(cudaMalloc(&tmp, tmp_bytes));
         CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, idx, perm, n, 0, 64, c->stream));
     }
+    CK(cudaMemsetAsync(c->d_ticket + 3, 0, sizeof(unsigned int), c->stream));
     prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, perm, nrows, ncols,
-                                                          ds.stride, cp);
+                                                          ds.stride, cp, c->d_ticket + 3);
     CK(cudaGetLastError());
+    unsigned int bad = 0;
+    CK(cudaMemcpyAsync(&bad, c->d_ticket + 3, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(tmp), cudaFree(keys), cudaFree(keys_out), cudaFree(idx), cudaFree(perm);
     CK(cudaFree(raw));
+    if (bad) {
+        cudaFree(ds.base);
+        ds = DataSet();
+        return fail(BUMP_E_INVALID, "input arrays must be finite and strictly positive (m1_det, q, d_L, pdraw)");
+    }
     return BUMP_OK;
 }
 
@@ -253,6 +266,8 @@ int build_plan(bump_ctx* c) {
     w.g_evt = std::max<int64_t>(1, (w.evt_stride + GROUP - 1) / GROUP);
     w.n_evt_groups = w.nobs * w.g_evt;
     w.n_groups = w.n_evt_groups + (w.sel_stride + GROUP - 1) / GROUP;
+    if (w.n_groups >= (int64_t(1) << 31))
+        return fail(BUMP_E_INVALID, "shard too large: more than 2^31 groups of 64 samples on one rank");
     // one CTA per SM (persistent); use fewer CTAs only when there are fewer groups than warps
     const int64_t max_warps = (int64_t)c->sm_count * STREAM_WARPS;
     if (const char* e = getenv("BUMP_GPW")) w.gpw = std::max<int64_t>(1, atoll(e));

@@ -8,6 +8,23 @@
 
 namespace bump {
 
+// Polynomial coefficients live in the constant bank: DFMA takes a c[bank][offset] operand directly, whereas a
+// literal whose low 32 bits are non-zero costs two UMOV/IMAD.MOV per use (measured: ~75 extra instructions per
+// sample, on an issue port that the FP64 stream already half fills).
+__constant__ double K_EXP[10] = {
+    23.083120654223414,       // [0] 16/ln2
+    0.04332169867120683,      // [1] ln2/16 high part (low 24 mantissa bits zero)
+    1.1378974990650914e-10,   // [2] ln2/16 low part
+    6755399441055744.0,       // [3] 1.5 * 2^52
+    0.0001984126984126984,    // [4] 1/7!
+    0.001388888888888889,     // [5] 1/6!
+    0.008333333333333333,     // [6] 1/5!
+    0.041666666666666664,     // [7] 1/4!
+    0.16666666666666666,      // [8] 1/3!
+    0.0,                      // [9] (unused)
+};
+__constant__ double K_L1P[4] = {1.0 / 7.0, -1.0 / 6.0, 0.2, 1.0 / 3.0};
+
 // ---- reciprocal of a positive normal double: MUFU.RCP64H seed (~2^-23) + 2 Newton steps
 __device__ __forceinline__ double frcp(const double x) {
     double r;
@@ -19,42 +36,39 @@ __device__ __forceinline__ double frcp(const double x) {
     return r;
 }
 
-// ---- exp(x) for finite x <= ~700 (x below -700 is clamped: result ~1e-304, callers treat it as zero).
-// x = n (ln2/16) + r, |r| <= ln2/32;  exp(x) = 2^(n>>4) * T[n&15] * (1 + p(r)),  T[j] = 2^(j/16) in shared
+// ---- exp(x) for finite x in (-1e5, 700); below about -700 the result saturates at ~1e-304 (callers treat it as
+// zero).  x = n (ln2/16) + r, |r| <= ln2/32;  exp(x) = 2^(n>>4) * T[n&15] * (1 + p(r)),  T[j] = 2^(j/16) in shared
 // memory (16 doubles = exactly one row of the 32 banks: any access pattern is conflict-free),
-// p = degree-7 Taylor polynomial of expm1 (truncation 0.0217^8/8! = 1.2e-18).
-__device__ __forceinline__ double fexp(double x, const double* __restrict__ expt) {
-    const double INV = 23.083120654223414;            // 16/ln2
-    const double C_HI = 0.04332169867120683;          // ln2/16, low 24 mantissa bits zero
-    const double C_LO = 1.1378974990650914e-10;
-    const double SHIFT = 6755399441055744.0;          // 1.5 * 2^52
-    x = fmax(x, -700.0);
-    double kd = fma(x, INV, SHIFT);
+// p = degree-7 Taylor polynomial of expm1 (truncation 0.0217^8/8! = 1.2e-18).  The underflow clamp is applied to
+// the integer n (one VIMNMX) instead of to x (DSETP + 2 FSEL on the FP64 pipe).
+__device__ __forceinline__ double fexp(const double x, const double* __restrict__ expt) {
+    double kd = fma(x, K_EXP[0], K_EXP[3]);
     const int n = __double2loint(kd);
-    kd -= SHIFT;
-    double r = fma(-kd, C_HI, x);
-    r = fma(-kd, C_LO, r);
-    double p = 0.0001984126984126984;                 // 1/7!
-    p = fma(p, r, 0.001388888888888889);
-    p = fma(p, r, 0.008333333333333333);
-    p = fma(p, r, 0.041666666666666664);
-    p = fma(p, r, 0.16666666666666666);
+    kd -= K_EXP[3];
+    double r = fma(-kd, K_EXP[1], x);
+    r = fma(-kd, K_EXP[2], r);
+    double p = K_EXP[4];
+    p = fma(p, r, K_EXP[5]);
+    p = fma(p, r, K_EXP[6]);
+    p = fma(p, r, K_EXP[7]);
+    p = fma(p, r, K_EXP[8]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p *= r;
     const double T = expt[n & 15];
     const double v = fma(T, p, T);
-    return __hiloint2double(__double2hiint(v) + ((n >> 4) << 20), __double2loint(v));
+    const int scale = (max(n, -16160) << 16) & 0xfff00000;   // ((n >> 4) << 20), n >= -1010 * 16
+    return __hiloint2double(__double2hiint(v) + scale, __double2loint(v));
 }
 
 // ---- log(1 + x) for 0 <= x <= 0.0046 (position inside one bin of the log-uniform z grid):
 // alternating series to x^7 (remainder 0.0046^8/8 = 2.5e-20)
 __device__ __forceinline__ double flog1p_small(const double x) {
-    double p = 1.0 / 7.0;
-    p = fma(p, x, -1.0 / 6.0);
-    p = fma(p, x, 0.2);
+    double p = K_L1P[0];
+    p = fma(p, x, K_L1P[1]);
+    p = fma(p, x, K_L1P[2]);
     p = fma(p, x, -0.25);
-    p = fma(p, x, 1.0 / 3.0);
+    p = fma(p, x, K_L1P[3]);
     p = fma(p, x, -0.5);
     p = fma(p, x, 1.0);
     return p * x;

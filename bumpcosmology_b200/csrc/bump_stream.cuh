@@ -268,62 +268,76 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
     if (warp >= wk.nwarps) return;
-    const int64_t g0 = (int64_t)warp * wk.gpw;
-    const int64_t g1 = min(g0 + wk.gpw, wk.n_groups);
+    // 32-bit group arithmetic (n_groups < 2^31 is checked on the host); 64-bit only to form addresses
+    const int n_groups = (int)wk.n_groups, n_evt_groups = (int)wk.n_evt_groups, g_evt = (int)wk.g_evt;
+    const int g0 = warp * (int)wk.gpw;
+    const int g1 = min(g0 + (int)wk.gpw, n_groups);
     if (g0 >= g1) return;
-    const int64_t e_first = group_event(wk, g0);
+    const int e_first = g0 < n_evt_groups ? g0 / g_evt : wk.nobs;
     double* rec = part + (size_t)rec_off[warp] * PART_STRIDE;
 
     // position of group g0: event e, group-in-event k
-    int64_t e = e_first;
-    int64_t k = (e < wk.nobs) ? g0 - e * wk.g_evt : g0 - wk.n_evt_groups;
+    int e = e_first;
+    int k = (e < wk.nobs) ? g0 - e * g_evt : g0 - n_evt_groups;
     ThreadAcc A;
     acc_init(A);
-    // first sample of group (ee, kk) in column 0, the column pitch of its set, and its number of sample pairs
-    auto locate = [&](const int64_t ee, const int64_t kk, const double*& p0, int64_t& pitch, int& pairs) {
+    // Lane l evaluates samples l ("x half") and 32+l ("y half") of each 64-sample group: two fully coalesced
+    // 64-bit loads per column.  The loads are software-pipelined at half-group granularity — y(g) is issued
+    // before x(g) is evaluated, x(g+1) before y(g) is evaluated — so every load has one sample evaluation
+    // (~1000 cycles) to land, at no extra register cost; L2 prefetches run one further group ahead.
+    struct Half {
+        double dl, m1, q, lm, lq, l1q, lpd;
+    };
+    auto locate = [&](const int ee, const int kk, const double*& p0, int64_t& pitch, int& count) {
         const bool is_sel = ee >= wk.nobs;
         const int64_t stride = is_sel ? wk.sel_stride : wk.evt_stride;
-        p0 = (is_sel ? cols.sel_base : cols.evt_base + ee * stride) + kk * GROUP;
+        p0 = (is_sel ? cols.sel_base : cols.evt_base + (int64_t)ee * stride) + (int64_t)kk * GROUP + lane;
         pitch = is_sel ? cols.sel_pitch : cols.evt_pitch;
-        pairs = (int)min((int64_t)GROUP, stride - kk * GROUP) >> 1;
+        count = (int)min((int64_t)GROUP, stride - (int64_t)kk * GROUP);
     };
-    auto load = [&](const double* p0, const int64_t pitch, const int col) {
-        return __ldg(reinterpret_cast<const double2*>(p0 + col * pitch) + lane);
+    auto load_half = [&](const double* p, const int64_t pitch, const bool on) {
+        Half h{1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0};   // zero-weight sentinel (source mass below mbh_min)
+        // volatile: keeps the load where it is written (ptxas otherwise sinks it to its first use to save
+        // registers, which exposes the full L2 latency once per group)
+        auto ld = [](const double* a) {
+            double v;
+            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
+            return v;
+        };
+        if (on) {
+            h.dl = ld(p + C_DL * pitch);
+            h.m1 = ld(p + C_M1D * pitch);
+            h.q = ld(p + C_Q * pitch);
+            h.lm = ld(p + C_LM * pitch);
+            h.lq = ld(p + C_LQ * pitch);
+            h.l1q = ld(p + C_L1Q * pitch);
+            h.lpd = ld(p + C_LPD * pitch);
+        }
+        return h;
     };
     const double* p0;
     int64_t pitch;
-    int pairs;
-    locate(e, k, p0, pitch, pairs);
-    const double2 SENT = make_double2(1.0, 1.0);
-    double2 dl = (lane < pairs) ? load(p0, pitch, C_DL) : SENT;
-    for (int64_t g = g0; g < g1; ++g) {
-        // ---- this group's remaining columns (d_L was fetched one group ahead)
-        const bool on = lane < pairs;
-        double2 m1 = SENT, q = SENT, lm = make_double2(0.0, 0.0), lq = lm, l1q = lm, lpd = lm;
-        if (on) {
-            m1 = load(p0, pitch, C_M1D);
-            q = load(p0, pitch, C_Q);
-            lm = load(p0, pitch, C_LM);
-            lq = load(p0, pitch, C_LQ);
-            l1q = load(p0, pitch, C_L1Q);
-            lpd = load(p0, pitch, C_LPD);
-        }
-        const double2 dl_cur = dl;
-        // ---- advance to the next group and prefetch its d_L (the first thing an evaluation needs)
-        int64_t e_next = e, k_next = k + 1;
-        const int64_t gcount = (e < wk.nobs) ? wk.g_evt : (wk.n_groups - wk.n_evt_groups);
-        if (k_next == gcount) {
+    int count;
+    locate(e, k, p0, pitch, count);
+    Half hx = load_half(p0, pitch, lane < count);
+    for (int g = g0; g < g1; ++g) {
+        const Half hy = load_half(p0 + 32, pitch, 32 + lane < count);
+        eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
+        // ---- advance to the next group and issue its x half; pull the group after it towards L2
+        int e_next = e, k_next = k + 1;
+        if (k_next == ((e < wk.nobs) ? g_evt : n_groups - n_evt_groups)) {
             k_next = 0;
             e_next = e + 1;
         }
         const bool more = g + 1 < g1;
         if (more) {
-            locate(e_next, k_next, p0, pitch, pairs);
-            dl = (lane < pairs) ? load(p0, pitch, C_DL) : SENT;
+            locate(e_next, k_next, p0, pitch, count);
+            hx = load_half(p0, pitch, lane < count);
+            const double* pf = p0 - lane + GROUP + (lane & 3) * 16;   // 4 lines of 128 B per column
+#pragma unroll
+            for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
         }
-        // ---- evaluate (inactive lanes carry the zero-weight sentinel: no divergence inside)
-        eval_sample<WA>(dl_cur.x, m1.x, q.x, lm.x, lq.x, l1q.x, lpd.x, s_blob, A);
-        eval_sample<WA>(dl_cur.y, m1.y, q.y, lm.y, lq.y, l1q.y, lpd.y, s_blob, A);
+        eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);
