@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -319,6 +320,7 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr) {
     tables_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_ticket + 2, c->use_wa ? 1 : 0);
     records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c));
+    CK(cudaMemcpyToSymbolAsync(K_SC, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL, 0, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0) {
         if (c->use_wa)
@@ -351,6 +353,26 @@ int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStrea
     return BUMP_OK;
 }
 
+// K_SC (constant bank) is shared by every context of a device: evaluations on one device are chained through an
+// event so that two contexts / streams never have an evaluation in flight at the same time.
+std::mutex g_dev_mutex;
+cudaEvent_t g_dev_event[64] = {};
+
+struct DeviceChain {
+    std::unique_lock<std::mutex> lock;
+    cudaEvent_t ev = nullptr;
+    cudaStream_t s;
+    DeviceChain(int device, cudaStream_t stream) : lock(g_dev_mutex), s(stream) {
+        if (device < 0 || device >= 64) return;
+        if (!g_dev_event[device]) cudaEventCreateWithFlags(&g_dev_event[device], cudaEventDisableTiming);
+        ev = g_dev_event[device];
+        cudaStreamWaitEvent(s, ev, 0);
+    }
+    ~DeviceChain() {
+        if (ev) cudaEventRecord(ev, s);
+    }
+};
+
 int ensure_ready(bump_ctx* c) {
     if (!c) return fail(BUMP_E_INVALID, "null context");
     if (int r = set_device(c)) return r;
@@ -376,8 +398,10 @@ int ensure_graph(bump_ctx* c) {
 }
 
 int run_once(bump_ctx* c) {   // d_theta -> d_out on the context stream
+    if (!(c->flags & BUMP_FLAG_NO_GRAPH))
+        if (int r = ensure_graph(c)) return r;
+    DeviceChain chain(c->device, c->stream);
     if (c->flags & BUMP_FLAG_NO_GRAPH) return launch_eval(c, c->d_theta, c->d_out, c->stream);
-    if (int r = ensure_graph(c)) return r;
     CK(cudaGraphLaunch(c->graph, c->stream));
     return BUMP_OK;
 }
@@ -484,6 +508,7 @@ int bump_eval(bump_ctx* c, const double* theta, double* out) {
 int bump_eval_device(bump_ctx* c, const double* theta_dev, double* out_dev, void* stream) {
     if (!theta_dev || !out_dev) return fail(BUMP_E_INVALID, "null theta/out");
     if (int r = ensure_ready(c)) return r;
+    DeviceChain chain(c->device, static_cast<cudaStream_t>(stream));
     return launch_eval(c, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -491,6 +516,7 @@ int bump_eval_partial_device(bump_ctx* c, const double* theta_dev, double* parti
                              void* stream) {
     if (!theta_dev || !partial_dev) return fail(BUMP_E_INVALID, "null theta/partial");
     if (int r = ensure_ready(c)) return r;
+    DeviceChain chain(c->device, static_cast<cudaStream_t>(stream));
     return launch_partial(c, theta_dev, partial_dev, neff_dev ? neff_dev : c->d_out + OUT_HEADER,
                           static_cast<cudaStream_t>(stream));
 }
@@ -509,7 +535,10 @@ int bump_eval_partial(bump_ctx* c, const double* theta, double* partial, double*
     const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
     memcpy(c->h_theta, theta, sizeof(double) * nth);
     CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
-    if (int r = launch_partial(c, c->d_theta, c->d_partial, c->d_out + OUT_HEADER, c->stream)) return r;
+    {
+        DeviceChain chain(c->device, c->stream);
+        if (int r = launch_partial(c, c->d_theta, c->d_partial, c->d_out + OUT_HEADER, c->stream)) return r;
+    }
     CK(cudaMemcpyAsync(partial, c->d_partial, sizeof(double) * PARTIAL_LEN, cudaMemcpyDeviceToHost, c->stream));
     if (neff_local && c->evt.nrows > 0)
         CK(cudaMemcpyAsync(neff_local, c->d_out + OUT_HEADER, sizeof(double) * c->evt.nrows, cudaMemcpyDeviceToHost,
@@ -581,6 +610,7 @@ int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms
     if (stream_ms) {   // the streaming kernel alone: events around each direct launch on the same stream
         float acc = 0.f;
         for (int i = 0; i < iters; ++i) {
+            DeviceChain chain(c->device, c->stream);
             if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, c->ev0, c->ev1)) return r;
             CK(cudaEventSynchronize(c->ev1));
             float ms = 0.f;

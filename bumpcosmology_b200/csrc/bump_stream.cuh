@@ -29,6 +29,11 @@ constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/;
 constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
+// The theta-dependent scalars of the current evaluation, copied device-to-device from the table blob right before
+// the launch: FP64 instructions take c[bank][offset] operands directly, so a scalar costs neither a shared-memory
+// load nor a register.  One evaluation at a time per device (bump_lib.cu chains launches through an event).
+__constant__ double K_SC[NSCAL];
+
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,29 +92,28 @@ struct MassEval {
     int b;
 };
 
-__device__ __forceinline__ void mass_eval(const double m, const double lm, const double* __restrict__ sc,
-                                          const double2* __restrict__ mass, const double* __restrict__ expt,
-                                          MassEval& o) {
-    const double y = (m - sc[S_M]) * sc[S_INV_DM];
+__device__ __forceinline__ void mass_eval(const double m, const double lm, const double2* __restrict__ mass,
+                                          const double* __restrict__ expt, MassEval& o) {
+    const double y = (m - K_SC[S_M]) * K_SC[S_INV_DM];
     const double e = fexp(-y, expt);
     const double s1 = frcp(1.0 + e);
     o.sgm = (e * s1) * m;
-    o.lrel = lm - sc[S_LOG_M];
-    o.EQ = fexp(-sc[S_C] * o.lrel, expt) * (sc[S_C2] * s1);
-    const double pos = (m - MIN_BH_MASS) * sc[S_INV_DMBH];
+    o.lrel = lm - K_SC[S_LOG_M];
+    o.EQ = fexp(-K_SC[S_C] * o.lrel, expt) * (K_SC[S_C2] * s1);
+    const double pos = (m - MIN_BH_MASS) * K_SC[S_INV_DMBH];
     int b = __double2int_rd(pos);
     b = min(max(b, 0), NM - 2);
     o.u = pos - (double)b;
     const double2 g = mass[MR_G * NM + b];
     const double eP = fexp(fma(o.u, g.y, g.x), expt);
-    o.EP = (m < sc[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
-    o.slope = g.y * sc[S_INV_DMBH];
+    o.EP = (m < K_SC[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
+    o.slope = g.y * K_SC[S_INV_DMBH];
     o.m = m;
     o.b = b;
 }
 
 // Feature contributions of one mass evaluation, weighted by wp = (weight of the sample) / (EP + EQ).
-__device__ __forceinline__ double mass_features(const MassEval& o, const double wp, const double* __restrict__ sc,
+__device__ __forceinline__ double mass_features(const MassEval& o, const double wp,
                                                 const double2* __restrict__ mass, double* __restrict__ a) {
     const double wQ = wp * o.EQ, wP = wp * o.EP;
     a[2 + F_SQ] += wQ;
@@ -124,14 +128,13 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
         a[2 + F_PA + k] = fma(wP, fma(o.u, t.y, t.x), a[2 + F_PA + k]);
     }
     // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c)
-    return fma(wPs, o.m, fma(wQs, sc[S_INV_DM], -sc[S_C] * wQ));
+    return fma(wPs, o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
 }
 
 template <bool WA>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
                                             const double* __restrict__ s_blob, ThreadAcc& A) {
-    const double* __restrict__ sc = s_blob + OFF_SCAL;
     const double* __restrict__ expt = s_blob + OFF_EXPT;
     const double2* __restrict__ cos = reinterpret_cast<const double2*>(s_blob + OFF_COS);
     const double* __restrict__ ctan = s_blob + OFF_CTAN;
@@ -144,14 +147,14 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     j = min(max(j, 0), SRCH_N - 1);
     int b = srch[j];
     while (b < NZ - 2 && x >= cos[CR_DL * NZ + b + 1].x) ++b;
-    const bool beyond = x > sc[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
+    const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     const double2 rdl = cos[CR_DL * NZ + b];
     double t = (x - rdl.x) * rdl.y;
     const double idl = beyond ? 0.0 : rdl.y;
     t = beyond ? 1.0 : t;
     // ---- position inside the z bin: 1+z = (1+z_b)(1 + t eps)
     const double2 rz = cos[CR_Z * NZ + b];
-    const double zeps = sc[S_ZEPS];
+    const double zeps = K_SC[S_ZEPS];
     const double te = t * zeps;
     const double u1 = frcp1p_small(te);
     const double ropz = rz.x * u1;                  // 1/(1+z)
@@ -173,7 +176,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double iddl = frcp(ddl);
     // ---- everything that is linear in precomputed logs: beta log(m1+m2) + log m1 + (lam-2) log1p(z) - log pdraw
     const double pair = lm1 + l1q;                  // log(m1+m2); the -beta log(60) is in the constant
-    const double lin = fma(sc[S_BETA], pair, lm1) + fma(sc[S_LAM2], L, -lpd);
+    const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM2], L, -lpd);
     if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
         const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
         A.a[0] *= s;
@@ -185,14 +188,14 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double E = valid ? fexp(lin - A.m, expt) : 0.0;
     A.nvalid += valid ? 1 : 0;
     // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
-    const double kappa = sc[S_KAPPA];
-    const double r = fexp(kappa * (L - sc[S_LOPZP]), expt);
+    const double kappa = K_SC[S_KAPPA];
+    const double r = fexp(kappa * (L - K_SC[S_LOPZP]), expt);
     const double sr = frcp(1.0 + r);
     const double sig = r * sr;
     // ---- mass function at both masses
     MassEval M1, M2;
-    mass_eval(m1, lm1, sc, mass, expt, M1);
-    mass_eval(m2, lm2, sc, mass, expt, M2);
+    mass_eval(m1, lm1, mass, expt, M1);
+    mass_eval(m2, lm2, mass, expt, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     // ---- the weight and its partial products
     const double base = (sr * iddl) * E;            // everything but the masses and dVc/dz
@@ -201,11 +204,11 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double bv = base * dvc;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    const double md = mass_features(M1, sum2 * bv, sc, mass, A.a) + mass_features(M2, sum1 * bv, sc, mass, A.a);
+    const double md = mass_features(M1, sum2 * bv, mass, A.a) + mass_features(M2, sum1 * bv, mass, A.a);
     // ---- d w / d t at fixed tables (times p), then the cosmological tangents
     const double lt = zeps * u1;                    // d log1p(z) / dt
     const double psig = p * sig;
-    const double pWt = fma(lt, fma(p, sc[S_RATE0], -fma(kappa, psig, md)), fma(rvc.y, p0, -(rdd.y * iddl) * p));
+    const double pWt = fma(lt, fma(p, K_SC[S_RATE0], -fma(kappa, psig, md)), fma(rvc.y, p0, -(rdd.y * iddl) * p));
     const double pWx = pWt * idl;                   // -pWx * (d dl-table/d theta)(t) = p (dw/dt)(dt/dtheta)
     A.a[2 + F_CZ] = fma(pWx, x, A.a[2 + F_CZ]);
     const double pid = p * iddl;
