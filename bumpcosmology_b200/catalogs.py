@@ -27,7 +27,11 @@ SHAPES = {
     "gwtc3": (69, 4096, 200_000, 20231, 1.5),
     "o4": (300, 8192, 1_000_000, 20232, 1.5),
     "o5": (5000, 10000, 10_000_000, 20233, 3.0),
+    # GWTC-3 shape for sampler runs: every sample and injection keeps its source-frame m2 well above the model's
+    # hard cut at mbh_min = 5 (see make_catalog: mass_floor)
+    "gwtc3_nuts": (69, 4096, 200_000, 20234, 1.5),
 }
+MASS_FLOOR = {"gwtc3_nuts": 8.0}
 
 _H_FID, _OM_FID = 0.6766, 0.30966
 _C_H100_GPC = 2.99792  # same constant as intensity_models.py:239
@@ -119,25 +123,33 @@ class _ZPDF:
         return np.interp(c, self.cdf, self.zg)
 
 
-def _draw_population(rng, n, zpdf, m1_lo=5.0):
+def _draw_population(rng, n, zpdf, m1_lo=5.0, m2_lo=5.0):
     z = zpdf.icdf(rng.uniform(size=n))
     mpdf = _PowerLaw(2.35, m1_lo, 500.0)
     m1 = mpdf.icdf(rng.uniform(size=n))
-    mt_pdf = _PowerLaw(2.0, m1 + 5.0, 2 * m1)
+    mt_pdf = _PowerLaw(2.0, m1 + m2_lo, 2 * m1)
     mt = mt_pdf.icdf(rng.uniform(size=n))
     q = np.minimum((mt - m1) / m1, 1.0)
     pdraw_mqz = mpdf.pdf(m1) * (mt_pdf.pdf(mt) * m1) * zpdf.pdf(z)
     return m1, q, z, pdraw_mqz
 
 
-def make_catalog(name="gwtc3", nobs=None, nsamp=None, nsel=None, seed=None, zmax=None, chunk_events=256):
-    """Build a seeded synthetic catalog. `name` picks a shape from SHAPES; explicit sizes override it."""
+def make_catalog(name="gwtc3", nobs=None, nsamp=None, nsel=None, seed=None, zmax=None, chunk_events=256,
+                 mass_floor=None):
+    """Build a seeded synthetic catalog. `name` picks a shape from SHAPES; explicit sizes override it.
+
+    mass_floor (default: MASS_FLOOR.get(name)): if set, posterior samples are redrawn until their source-frame m2
+    (at the fiducial cosmology) is >= mass_floor, and injections are drawn with m1, m2 >= mass_floor.  The
+    reference's mass function is cut hard at mbh_min = 5 (intensity_models.py:149): samples that cross the cut as
+    (h, Om, w) move make logL discontinuous while its gradient (JAX's as well as ours) ignores the jumps, which
+    stalls any HMC sampler.  Real PE samples sit away from the cut; the sampler workload mimics that."""
     d_nobs, d_nsamp, d_nsel, d_seed, d_zmax = SHAPES.get(name, SHAPES["gwtc3"])
     nobs = d_nobs if nobs is None else nobs
     nsamp = d_nsamp if nsamp is None else nsamp
     nsel = d_nsel if nsel is None else nsel
     seed = d_seed if seed is None else seed
     zmax = d_zmax if zmax is None else zmax
+    mass_floor = MASS_FLOOR.get(name) if mass_floor is None else mass_floor
     rng = np.random.default_rng(seed)
     cosmo = _FiducialCosmology()
 
@@ -150,7 +162,7 @@ def make_catalog(name="gwtc3", nobs=None, nsamp=None, nsel=None, seed=None, zmax
     filled = 0
     while filled < nobs:
         m1, q, z, _ = _draw_population(rng, 4 * (nobs - filled) + 16, zpdf_evt, m1_lo=8.0)
-        ok = (q * m1 >= 7.0) & (m1 <= 120.0)
+        ok = (q * m1 >= (7.0 if mass_floor is None else mass_floor + 6.0)) & (m1 <= 120.0)
         k = min(int(ok.sum()), nobs - filled)
         m1_t[filled:filled + k] = m1[ok][:k]
         q_t[filled:filled + k] = q[ok][:k]
@@ -179,6 +191,24 @@ def make_catalog(name="gwtc3", nobs=None, nsamp=None, nsel=None, seed=None, zmax
             qq[bad] = redraw
             bad = (qq <= 0) | (qq > 1)
         log_dls = log_dl_obs[lo:hi, None] + s_dl[lo:hi, None] * rng.standard_normal(shp)
+        if mass_floor is not None:   # redraw samples whose source-frame m2 (fiducial cosmology) is below the floor
+            for _ in range(200):
+                m1d = np.exp(log_mcs) / (qq ** 0.6 / (1 + qq) ** 0.2)
+                zz = np.interp(np.exp(log_dls), cosmo.dl, cosmo.z)
+                bad = qq * m1d / (1 + zz) < mass_floor
+                if not bad.any():
+                    break
+                nb = int(bad.sum())
+                b_mc = np.broadcast_to(log_mc_obs[lo:hi, None], shp)[bad]
+                b_smc = np.broadcast_to(s_mc[lo:hi, None], shp)[bad]
+                b_q = np.broadcast_to(q_obs[lo:hi, None], shp)[bad]
+                b_sq = np.broadcast_to(s_q[lo:hi, None], shp)[bad]
+                b_dl = np.broadcast_to(log_dl_obs[lo:hi, None], shp)[bad]
+                b_sdl = np.broadcast_to(s_dl[lo:hi, None], shp)[bad]
+                log_mcs[bad] = b_mc + b_smc * rng.standard_normal(nb)
+                qn = b_q + b_sq * rng.standard_normal(nb)
+                qq[bad] = np.where((qn > 0) & (qn <= 1), qn, qq[bad])
+                log_dls[bad] = b_dl + b_sdl * rng.standard_normal(nb)
         qs[lo:hi] = qq
         m1s_det[lo:hi] = np.exp(log_mcs) / (qq ** 0.6 / (1 + qq) ** 0.2)
         dls[lo:hi] = np.exp(log_dls)
@@ -186,7 +216,8 @@ def make_catalog(name="gwtc3", nobs=None, nsamp=None, nsel=None, seed=None, zmax
 
     # ---- found injections
     zpdf_inj = _ZPDF(cosmo, 3.5)
-    m1, q, z, pdraw_mqz = _draw_population(rng, nsel, zpdf_inj)
+    fl = 5.0 if mass_floor is None else mass_floor
+    m1, q, z, pdraw_mqz = _draw_population(rng, nsel, zpdf_inj, m1_lo=fl, m2_lo=fl)
     jac = 1.0 / (1 + z) / (cosmo.f(z, cosmo.dc) + (1 + z) * cosmo.dH / cosmo.f(z, cosmo.E))  # weighting.py:180
     return Catalog(
         m1s_det=m1s_det, qs=qs, dls=dls, pdraw=pdraw,

@@ -258,8 +258,13 @@ __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ ou
 // bulk copy, one mbarrier) no warp ever synchronises with another: warp w walks its range of 64-sample groups
 // [w*gpw, (w+1)*gpw), lane l evaluating samples 2l and 2l+1 of each group (one 128-bit load per column), and
 // flushes a record whenever the event changes.
+#ifdef BUMP_STREAM_MAXREG
+#define BUMP_STREAM_BOUNDS __maxnreg__(BUMP_STREAM_MAXREG)
+#else
+#define BUMP_STREAM_BOUNDS __launch_bounds__(STREAM_THREADS, 1)
+#endif
 template <bool WA>
-__global__ void __launch_bounds__(STREAM_THREADS, 1)
+__global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
