@@ -43,7 +43,7 @@ constexpr int SRCH_OCTAVES = 21;          // 2^-8 .. 2^13 Gpc
 constexpr int SRCH_N = SRCH_OCTAVES << SRCH_MBITS;   // 5376 uint16 entries
 constexpr int SRCH_DOUBLES = SRCH_N / 4;
 
-constexpr int NEXPT = 16;    // 2^(j/16), one 128-byte row of shared memory (bump_math.cuh fexp)
+constexpr int NEXPT = 64;    // 2^(j/64) (bump_math.cuh fexp)
 constexpr int OFF_SCAL = 0;
 constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT]
 constexpr int OFF_COS = OFF_EXPT + NEXPT;               // double2 cos[NCPAIR][NZ]

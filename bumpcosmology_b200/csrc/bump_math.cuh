@@ -2,26 +2,26 @@
 // the kernel needs.  Each is accurate to ~1-2 ulp on its stated domain (tests/test_gpu_parity.py::test_device_math
 // compares them with CUDA libm through bump_debug_math).  The FP64 pipe (64 lanes/clk/SM on B200) is the
 // binding resource of the fp64 path, so these are sized in DFMA-pipe instructions:
-//   fexp  12   (libm exp ~18-20 + branches)      frcp  4 + MUFU.RCP64H   (IEEE division ~24)
+//   fexp  10   (libm exp ~18-20 + branches)      frcp  4 + MUFU.RCP64H   (IEEE division ~24)
 #pragma once
 #include <math.h>
+
+#include "bump_layout.cuh"
 
 namespace bump {
 
 // Polynomial coefficients live in the constant bank: DFMA takes a c[bank][offset] operand directly, whereas a
 // literal whose low 32 bits are non-zero costs two UMOV/IMAD.MOV per use (measured: ~75 extra instructions per
 // sample, on an issue port that the FP64 stream already half fills).
-__constant__ double K_EXP[10] = {
-    23.083120654223414,       // [0] 16/ln2
-    0.04332169867120683,      // [1] ln2/16 high part (low 24 mantissa bits zero)
-    1.1378974990650914e-10,   // [2] ln2/16 low part
+__constant__ double K_EXP[8] = {
+    92.33248261689366,        // [0] 64/ln2
+    0.010830424609594047,     // [1] ln2/64 high part (low 26 mantissa bits zero)
+    8.66550983900947e-11,     // [2] ln2/64 low part
     6755399441055744.0,       // [3] 1.5 * 2^52
-    0.0001984126984126984,    // [4] 1/7!
-    0.001388888888888889,     // [5] 1/6!
-    0.008333333333333333,     // [6] 1/5!
-    0.041666666666666664,     // [7] 1/4!
-    0.16666666666666666,      // [8] 1/3!
-    0.0,                      // [9] (unused)
+    0.008333333333333333,     // [4] 1/5!
+    0.041666666666666664,     // [5] 1/4!
+    0.16666666666666666,      // [6] 1/3!
+    0.0,
 };
 __constant__ double K_L1P[4] = {1.0 / 7.0, -1.0 / 6.0, 0.2, 1.0 / 3.0};
 
@@ -37,10 +37,10 @@ __device__ __forceinline__ double frcp(const double x) {
 }
 
 // ---- exp(x) for finite x in (-1e5, 700); below about -700 the result saturates at ~1e-304 (callers treat it as
-// zero).  x = n (ln2/16) + r, |r| <= ln2/32;  exp(x) = 2^(n>>4) * T[n&15] * (1 + p(r)),  T[j] = 2^(j/16) in shared
-// memory (16 doubles = exactly one row of the 32 banks: any access pattern is conflict-free),
-// p = degree-7 Taylor polynomial of expm1 (truncation 0.0217^8/8! = 1.2e-18).  The underflow clamp is applied to
-// the integer n (one VIMNMX) instead of to x (DSETP + 2 FSEL on the FP64 pipe).
+// zero).  x = n (ln2/64) + r, |r| <= ln2/128;  exp(x) = 2^(n>>6) * T[n&63] * (1 + p(r)),  T[j] = 2^(j/64) in shared
+// memory (512 bytes; neighbouring lanes carry neighbouring samples, so their arguments mostly share an entry),
+// p = degree-5 Taylor polynomial of expm1 (truncation 0.0054^6/6! = 3.5e-17).  The underflow clamp is applied to
+// the integer n (one VIMNMX) instead of to x (DSETP + 2 FSEL on the FP64 pipe).  10 FP64-pipe instructions.
 __device__ __forceinline__ double fexp(const double x, const double* __restrict__ expt) {
     double kd = fma(x, K_EXP[0], K_EXP[3]);
     const int n = __double2loint(kd);
@@ -50,14 +50,12 @@ __device__ __forceinline__ double fexp(const double x, const double* __restrict_
     double p = K_EXP[4];
     p = fma(p, r, K_EXP[5]);
     p = fma(p, r, K_EXP[6]);
-    p = fma(p, r, K_EXP[7]);
-    p = fma(p, r, K_EXP[8]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p *= r;
-    const double T = expt[n & 15];
+    const double T = expt[n & (NEXPT - 1)];
     const double v = fma(T, p, T);
-    const int scale = (max(n, -16160) << 16) & 0xfff00000;   // ((n >> 4) << 20), n >= -1010 * 16
+    const int scale = (max(n, -1010 * NEXPT) << 14) & 0xfff00000;   // ((n >> 6) << 20)
     return __hiloint2double(__double2hiint(v) + scale, __double2loint(v));
 }
 
