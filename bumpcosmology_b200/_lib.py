@@ -16,7 +16,7 @@ OUT_DLOGLIKE, OUT_DLOG_MU = 4, 19
 OUT_NVALID_EVT, OUT_NVALID_SEL, OUT_NOBS, OUT_NSEL = 34, 35, 36, 37
 OUT_HEADER = 40
 PARTIAL_LEN = 128
-FLAG_WA, FLAG_NO_GRAPH, FLAG_NO_SORT = 1, 2, 4
+FLAG_WA, FLAG_NO_GRAPH, FLAG_NO_SORT, FLAG_FIXED_COSMO = 1, 2, 4, 8
 
 _dp = C.POINTER(C.c_double)
 
@@ -29,6 +29,7 @@ SIGNATURES = {
     "bump_ctx_destroy": (None, [C.c_void_p]),
     "bump_upload_events": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp]),
     "bump_upload_injections": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_double]),
+    "bump_set_fixed_dvdzdt": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "bump_out_len": (C.c_int64, [C.c_void_p]),
     "bump_eval": (C.c_int, [C.c_void_p, _dp, _dp]),
     "bump_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

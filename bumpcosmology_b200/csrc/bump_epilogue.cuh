@@ -43,6 +43,7 @@ __host__ __device__ inline void grad_from_features(const double* phi, const doub
     g[T_KAPPA] = -(phi[F_SIGL] - sc[S_LOPZP] * phi[F_SIG]) + n * sc[S_LNV_KAPPA];
     g[T_ZP] = phi[F_SIG] * kappa / (1.0 + zp) + n * sc[S_LNV_ZP];
     g[T_WA] = (sc[S_USE_WA] != 0.0) ? phi[F_WA] : 0.0;
+    if (sc[S_FIXED] != 0.0) g[T_H] = g[T_OM] = g[T_W] = g[T_WA] = 0.0;   // pop_model: the cosmology is not a parameter
 }
 
 // partials: [nranks][PARTIAL_LEN] in rank order -> out[OUT_HEADER]

@@ -80,6 +80,7 @@ enum Scal {
     S_LAM2 = 41,     // lam - 2
     S_RATE0 = 42,    // lam - 3 - beta
     S_BAD = 43,      // 1 if theta or any table entry is not finite (outputs are then NaN)
+    S_FIXED = 44,    // 1 in fixed-cosmology mode (pop_model): no gradient w.r.t. (h, Om, w)
 };
 
 // ---- per-sample gradient features accumulated by the streaming kernel (DESIGN.md has the algebra)

@@ -120,7 +120,7 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
                                        const double* __restrict__ dl, const double* __restrict__ pd,
                                        const unsigned int* __restrict__ perm, const int64_t nrows,
                                        const int64_t ncols, const int64_t stride, ColumnPtrs out,
-                                       unsigned int* __restrict__ bad) {
+                                       unsigned int* __restrict__ bad, const double* __restrict__ fixed_tab) {
     const int64_t total = nrows * stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / stride, c = i - r * stride;
@@ -132,13 +132,28 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
             if (!(vm > 0.0 && vq > 0.0 && dl[s] > 0.0 && pd[s] > 0.0 && isfinite(vm) && isfinite(vq) &&
                   isfinite(dl[s]) && isfinite(pd[s])))
                 atomicOr(bad, 1u);
-            out.c[C_DL][i] = dl[s];
             out.c[C_M1D][i] = vm;
             out.c[C_Q][i] = vq;
             out.c[C_LM][i] = log(vm);
             out.c[C_LQ][i] = log(vq);
             out.c[C_L1Q][i] = log1p(vq);
-            out.c[C_LPD][i] = log(pd[s]);
+            if (!fixed_tab) {
+                out.c[C_DL][i] = dl[s];
+                out.c[C_LPD][i] = log(pd[s]);
+            } else {
+                // fixed cosmology (pop_model, intensity_models.py:313-355): `dl` holds z; column 0 becomes log1p(z)
+                // and log dVdzdt(z) = log interp(z, zinterp, dVdzdt_interp) (:332) is folded into the pdraw column
+                const double z = dl[s], lz = log1p(z);
+                int k = min(max((int)floor(lz / ZSTEP), 0), NZ - 2);
+                while (k < NZ - 2 && expm1((k + 1) * ZSTEP) <= z) ++k;    // searchsorted(side='right') on zinterp
+                while (k > 0 && expm1(k * ZSTEP) > z) --k;
+                const double z0 = expm1(k * ZSTEP), z1 = (k + 1 == NZ - 1) ? expm1(LOG_ZMAX1) : expm1((k + 1) * ZSTEP);
+                double v = fixed_tab[k] + (z - z0) / (z1 - z0) * (fixed_tab[k + 1] - fixed_tab[k]);
+                if (z > z1 && k == NZ - 2) v = fixed_tab[NZ - 1];
+                out.c[C_DL][i] = lz;
+                out.c[C_LPD][i] = log(pd[s]) - log(v);
+                if (!(v > 0.0)) out.c[C_M1D][i] = 1.0;   // log dVdzdt = -inf: zero weight (sentinel mass)
+            }
         } else {   // sentinel padding: source mass 1/(1+z) < mbh_min -> weight exactly zero (-inf log weight)
             out.c[C_DL][i] = 1.0;
             out.c[C_M1D][i] = 1.0;
@@ -163,6 +178,9 @@ struct bump_ctx {
     int device = 0;
     uint32_t flags = 0;
     bool use_wa = false;
+    bool fixed = false;               // fixed-cosmology mode (pop_model)
+    double* d_fixed_tab = nullptr;    // dVdzdt on the 1024-knot z grid
+    bool fixed_tab_set = false;
     cudaStream_t stream = nullptr;
     DataSet evt, sel;
     double ndraw = 1.0;
@@ -206,6 +224,8 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
                const double* dl, const double* pd) {
     if (nrows < 0 || ncols < 0) return fail(BUMP_E_INVALID, "negative size");
     if (nrows * ncols > 0 && (!m1d || !q || !dl || !pd)) return fail(BUMP_E_INVALID, "null data pointer");
+    if (c->fixed && !c->fixed_tab_set)
+        return fail(BUMP_E_INVALID, "fixed-cosmology mode: call bump_set_fixed_dvdzdt before uploading data");
     if (int r = set_device(c)) return r;
     cudaFree(ds.base);
     ds = DataSet();
@@ -242,7 +262,8 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     }
     CK(cudaMemsetAsync(c->d_ticket + 3, 0, sizeof(unsigned int), c->stream));
     prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, perm, nrows, ncols,
-                                                          ds.stride, cp, c->d_ticket + 3);
+                                                          ds.stride, cp, c->d_ticket + 3,
+                                                          c->fixed ? c->d_fixed_tab : nullptr);
     CK(cudaGetLastError());
     unsigned int bad = 0;
     CK(cudaMemcpyAsync(&bad, c->d_ticket + 3, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
@@ -312,6 +333,7 @@ EvalConsts consts_of(const bump_ctx* c) {
     ec.log_nsamp = log((double)std::max<int64_t>(c->evt.ncols, 1));
     ec.log_ndraw = log(c->ndraw);
     ec.use_wa = c->use_wa ? 1 : 0;
+    ec.fixed = c->fixed ? 1 : 0;
     return ec;
 }
 
@@ -323,12 +345,15 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
     CK(cudaMemcpyToSymbolAsync(K_SC, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL, 0, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0) {
-        if (c->use_wa)
-            stream_kernel<true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work, c->d_rec_off,
-                                                                                   c->d_blob, c->d_part);
+        if (c->fixed)
+            stream_kernel<false, true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
+                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
+        else if (c->use_wa)
+            stream_kernel<true, false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
+                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
         else
-            stream_kernel<false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work,
-                                                                                    c->d_rec_off, c->d_blob, c->d_part);
+            stream_kernel<false, false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
+                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
     }
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
@@ -436,6 +461,11 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     c->device = device;
     c->flags = flags;
     c->use_wa = (flags & BUMP_FLAG_WA) != 0;
+    c->fixed = (flags & BUMP_FLAG_FIXED_COSMO) != 0;
+    if (c->fixed && c->use_wa) {
+        delete c;
+        return fail(BUMP_E_INVALID, "BUMP_FLAG_FIXED_COSMO and BUMP_FLAG_WA are mutually exclusive");
+    }
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
@@ -449,8 +479,10 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    CK(cudaFuncSetAttribute(stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    CK(cudaMalloc(&c->d_fixed_tab, sizeof(double) * NZ));
+    CK(cudaFuncSetAttribute(stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
     *out = c;
     return BUMP_OK;
 }
@@ -469,6 +501,7 @@ void bump_ctx_destroy(bump_ctx* c) {
     cudaFree(c->d_partial);
     cudaFree(c->d_gather);
     cudaFree(c->d_ticket);
+    cudaFree(c->d_fixed_tab);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -488,6 +521,16 @@ int bump_upload_injections(bump_ctx* c, int64_t nsel, const double* m1s_det_sel,
     if (!(ndraw > 0.0)) return fail(BUMP_E_INVALID, "ndraw must be positive");
     c->ndraw = ndraw;
     return upload_set(c, c->sel, nsel > 0 ? 1 : 0, nsel, m1s_det_sel, qs_sel, dls_sel, pdraw_sel);
+}
+
+int bump_set_fixed_dvdzdt(bump_ctx* c, const double* dvdzdt, int64_t n) {
+    if (!c || !dvdzdt) return fail(BUMP_E_INVALID, "null argument");
+    if (!c->fixed) return fail(BUMP_E_INVALID, "context was not created with BUMP_FLAG_FIXED_COSMO");
+    if (n != NZ) return fail(BUMP_E_INVALID, "the dVdzdt table must have 1024 entries (zinterp of intensity_models.py:324)");
+    if (int r = set_device(c)) return r;
+    CK(cudaMemcpy(c->d_fixed_tab, dvdzdt, sizeof(double) * NZ, cudaMemcpyHostToDevice));
+    c->fixed_tab_set = true;
+    return BUMP_OK;
 }
 
 int64_t bump_out_len(const bump_ctx* c) { return c ? OUT_HEADER + c->evt.nrows : 0; }

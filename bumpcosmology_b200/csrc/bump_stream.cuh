@@ -131,6 +131,52 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
     return fma(wPs, o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
 }
 
+// Fixed-cosmology variant (the reference's `pop_model`, intensity_models.py:313-355): the sample carries source-frame
+// (m1, q) and log1p(z) directly, `lpd` = log pdraw - log dVdzdt(z) was folded at upload, and there is no d_L
+// inversion, no Jacobian and no cosmological gradient.
+template <bool WA>
+__device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
+                                                  const double lq, const double l1q, const double lpd,
+                                                  const double* __restrict__ s_blob, ThreadAcc& A) {
+    const double* __restrict__ expt = s_blob + OFF_EXPT;
+    const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
+    double m2 = q * m1;
+    double lm2 = lm1 + lq;
+    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);   // :149
+    if (!valid) {
+        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
+    }
+    const double pair = lm1 + l1q;
+    const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM], L, -lpd);   // :332 (no (1+z)^-2 Jacobian here)
+    if (valid && lin - A.m > RESCALE_GAP) {
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
+        A.a[0] *= s;
+        A.a[1] *= s * s;
+#pragma unroll
+        for (int k = 2; k < NACC; ++k) A.a[k] *= s;
+        A.m = lin;
+    }
+    const double E = valid ? fexp(lin - A.m, expt) : 0.0;
+    A.nvalid += valid ? 1 : 0;
+    const double r = fexp(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), expt);
+    const double sr = frcp(1.0 + r);
+    MassEval M1, M2;
+    mass_eval(m1, lm1, mass, expt, M1);
+    mass_eval(m2, lm2, mass, expt, M2);
+    const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
+    const double base = sr * E;
+    const double p = (sum1 * sum2) * base;
+    A.a[0] += p;
+    A.a[1] = fma(p, p, A.a[1]);
+    mass_features(M1, sum2 * base, mass, A.a);
+    mass_features(M2, sum1 * base, mass, A.a);
+    const double psig = p * (r * sr);
+    A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
+    A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
+    A.a[2 + F_SIG] += psig;
+    A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
+}
+
 template <bool WA>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
@@ -263,7 +309,7 @@ __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ ou
 #else
 #define BUMP_STREAM_BOUNDS __launch_bounds__(STREAM_THREADS, 1)
 #endif
-template <bool WA>
+template <bool WA, bool FIXED>
 __global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part) {
@@ -330,7 +376,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     Half hx = load_half(p0, pitch, lane < count);
     for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32, pitch, 32 + lane < count);
-        eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
+        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
+        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
         // ---- advance to the next group and issue its x half; pull the group after it towards L2
         int e_next = e, k_next = k + 1;
         if (k_next == ((e < wk.nobs) ? g_evt : n_groups - n_evt_groups)) {
@@ -345,7 +392,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
 #pragma unroll
             for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
         }
-        eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
+        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
+        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);

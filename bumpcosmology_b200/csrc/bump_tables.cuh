@@ -28,6 +28,7 @@ struct EvalConsts {   // theta-independent numbers the prologue copies into the 
     double log_nsamp;
     double log_ndraw;
     int use_wa;
+    int fixed;
 };
 
 template <int NV>
@@ -271,6 +272,7 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
     scal[S_LOG_NSAMP] = ec.log_nsamp;
     scal[S_LOG_NDRAW] = ec.log_ndraw;
     scal[S_USE_WA] = (double)ec.use_wa;
+    scal[S_FIXED] = (double)ec.fixed;
     scal[S_DL_FIRST] = aux[AUX_DL + 0];
     scal[S_EXP_LPN] = exp(lpn.v);
     scal[S_ZEPS] = expm1(ZSTEP);

@@ -134,6 +134,52 @@ class PopCosmoModel:
         self._local.close()
 
 
+FIXED_SITES = ("a", "b", "c", "mpisn", "dmbhmax", "sigma", "beta", "log_fpl", "lam", "dkappa", "zp", "R_unit")
+
+
+class PopModel:
+    """The reference's fixed-cosmology model `pop_model` (intensity_models.py:313-355) bound to its data:
+    source-frame (m1s, qs, zs, pdraw) and the theta-independent table `dVdzdt_interp` that the reference builds from
+    astropy's Planck18 on zinterp = expm1(linspace(log1p(0), log1p(100), 1024)) (:323-325; astropy is not
+    available here, so the caller supplies the 1024 numbers).  Sites: mass_parameters, redshift_parameters, R_unit."""
+
+    def __init__(self, m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw, dVdzdt_interp, device=0):
+        self.like = Hyperlikelihood(m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw, device=device,
+                                    fixed_dvdzdt=dVdzdt_interp)
+
+    def evaluate(self, sites):
+        if isinstance(sites, dict):
+            x = np.array([float(sites.get(k, 0.0)) for k in FIXED_SITES])
+        else:
+            x = np.asarray(sites, dtype=np.float64).ravel()
+        full = np.concatenate([[0.7, 0.3, -1.0], x[:11]])     # (h, Om, w) are placeholders: ignored by the kernel
+        theta = priors.theta_from_sites(full)
+        r = self.like(theta)
+        nobs = r.nobs
+        mu_sel = math.exp(r.log_mu_sel) if math.isfinite(r.log_mu_sel) else float("nan")
+        return {
+            "loglike": r.loglike, "selfactor": -nobs * r.log_mu_sel, "mbhmax": theta[7], "fpl": theta[9],
+            "kappa": theta[12], "log_mu_sel": r.log_mu_sel, "neff_sel": r.neff_sel, "neff": r.neff,
+            "R": nobs / mu_sel + math.sqrt(nobs) / mu_sel * (x[11] if x.shape[0] > 11 else 0.0),
+            "dloglike_dsite": priors.grad_sites_from_theta(r.dloglike, theta)[3:],
+            "dselfactor_dsite": -nobs * priors.grad_sites_from_theta(r.dlog_mu_sel, theta)[3:],
+            "nobs": nobs, "theta": theta,
+        }
+
+    __call__ = evaluate
+
+    def close(self):
+        self.like.close()
+
+
+def pop_model(m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw, dVdzdt_interp=None, **kwargs):
+    """Same positional signature as the reference's fixed-cosmology model (intensity_models.py:313)."""
+    if dVdzdt_interp is None:
+        raise ValueError("pop_model needs dVdzdt_interp (1024 values on the reference's zinterp grid): the reference "
+                         "takes it from astropy's Planck18, which is not available here")
+    return PopModel(m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw, dVdzdt_interp, **kwargs)
+
+
 def pop_cosmo_model(m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, **kwargs):
     """Same positional signature as the reference model (intensity_models.py:357); returns the bound model."""
     return PopCosmoModel(m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, **kwargs)

@@ -84,15 +84,19 @@ class Hyperlikelihood:
     """
 
     def __init__(self, m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, device=0,
-                 wa=False, graph=True, sort=True):
+                 wa=False, graph=True, sort=True, fixed_dvdzdt=None):
         self.lib = _lib.load()
         self.wa = bool(wa)
         self.ntheta = _lib.NTHETA_MAX if wa else _lib.NTHETA
         self.device = int(device)
         self._ctx = C.c_void_p()
+        self.fixed = fixed_dvdzdt is not None
         flags = ((_lib.FLAG_WA if wa else 0) | (0 if graph else _lib.FLAG_NO_GRAPH)
-                 | (0 if sort else _lib.FLAG_NO_SORT))
+                 | (0 if sort else _lib.FLAG_NO_SORT) | (_lib.FLAG_FIXED_COSMO if self.fixed else 0))
         _lib.check(self.lib.bump_ctx_create(C.byref(self._ctx), self.device, flags))
+        if self.fixed:   # pop_model (intensity_models.py:313-355): arguments are (m1s, qs, zs, pdraw, ...) source frame
+            tab = _c64(fixed_dvdzdt).ravel()
+            _lib.check(self.lib.bump_set_fixed_dvdzdt(self._ctx, _lib.as_dp(tab), tab.shape[0]))
         ev = [_c64(x) for x in (m1s_det, qs, dls, pdraw)]
         if ev[0].ndim == 1:
             ev = [x.reshape(1, -1) if x.size else x.reshape(0, 0) for x in ev]

@@ -49,6 +49,8 @@ extern "C" {
 #define BUMP_FLAG_WA 1u        /* w0-wa (CPL) dark energy: theta has 15 entries */
 #define BUMP_FLAG_NO_GRAPH 2u  /* launch kernels directly instead of replaying a CUDA graph */
 #define BUMP_FLAG_NO_SORT 4u   /* keep the caller's sample order inside each event (default: locality sort at upload) */
+#define BUMP_FLAG_FIXED_COSMO 8u /* fixed cosmology = the reference's pop_model (intensity_models.py:313-355): the upload
+                                  * functions then take SOURCE-frame (m1s, qs, zs, pdraw) and theta[0..2] are ignored */
 
 typedef struct bump_ctx bump_ctx;
 
@@ -72,6 +74,11 @@ int bump_upload_events(bump_ctx* ctx, int64_t nobs, int64_t nsamp, const double*
  * (m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw of intensity_models.py:357; run_cosmo_fit.py:49). */
 int bump_upload_injections(bump_ctx* ctx, int64_t nsel, const double* m1s_det_sel, const double* qs_sel,
                            const double* dls_sel, const double* pdraw_sel, double ndraw);
+
+/* Fixed-cosmology mode only, before the uploads: the theta-independent table dVdzdt_interp (1024 doubles) on
+ * zinterp = expm1(linspace(log1p(0), log1p(100), 1024)) that pop_model builds from astropy's Planck18
+ * (intensity_models.py:323-325); log interp(z, zinterp, dVdzdt_interp) (:332) is folded into the samples at upload. */
+int bump_set_fixed_dvdzdt(bump_ctx* ctx, const double* dvdzdt_interp, int64_t n);
 
 /* Number of doubles bump_eval writes: BUMP_OUT_HEADER + nobs_local. */
 int64_t bump_out_len(const bump_ctx* ctx);

@@ -304,6 +304,43 @@ def evaluate(theta, data, grad=True, wa=None, event_chunk=None):
     return out
 
 
+def evaluate_fixed(theta, data, dvdzdt_interp, grad=True):
+    """Fixed-cosmology variant = the reference's `pop_model` (intensity_models.py:313-355).
+
+    theta: the same 14-vector (entries 0..2 = h, Om, w are ignored); data: (m1s, qs, zs, pdraw, m1s_sel, qs_sel,
+    zs_sel, pdraw_sel, Ndraw) in the SOURCE frame; dvdzdt_interp: the theta-independent table of :325 on
+    zinterp = expm1(linspace(log1p(0), log1p(100), 1024)) (:324)."""
+    m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw = data
+    th = torch.tensor(np.asarray(theta, dtype=np.float64)[:NTHETA], requires_grad=grad)
+    p = split_theta(th)
+    log_dN = JointDensity(p["a"], p["b"], p["c"], p["mpisn"], p["mbhmax"], p["sigma"], p["fpl"], p["beta"],
+                          p["lam"], p["kappa"], p["zp"])
+    zinterp = torch.expm1(torch.as_tensor(np.linspace(np.log1p(0), np.log1p(ZMAX), NINTERP)))
+    tab = _t(dvdzdt_interp)
+
+    def lw(m1, q, z, pd):   # :332 / :336
+        m1, q, z, pd = map(_t, (m1, q, z, pd))
+        return log_dN(m1, q, z) + torch.log(interp(z, zinterp, tab)) - torch.log(pd)
+
+    w = lw(m1s, qs, zs, pdraw)
+    nobs, nsamp = w.shape
+    lse = torch.logsumexp(w, dim=1)
+    loglike = (lse - math.log(nsamp)).sum()
+    neff = torch.exp(2 * lse - torch.logsumexp(2 * w, dim=1))
+    ws = lw(m1s_sel, qs_sel, zs_sel, pdraw_sel)
+    log_nd = math.log(float(Ndraw))
+    log_mu = torch.logsumexp(ws, 0) - log_nd
+    log_mu2 = torch.logsumexp(2 * ws, 0) - 2 * log_nd
+    log_s2 = log_mu2 + torch.log1p(-torch.exp(2 * log_mu - log_nd - log_mu2))
+    out = {"loglike": float(loglike.detach()), "log_mu_sel": float(log_mu.detach()), "log_mu2": float(log_mu2.detach()),
+           "neff_sel": float(torch.exp(2 * log_mu - log_s2).detach()), "neff": neff.detach().numpy().copy(),
+           "nobs": nobs, "selfactor": -nobs * float(log_mu.detach())}
+    if grad:
+        out["dloglike"] = torch.autograd.grad(loglike, th, retain_graph=True)[0].numpy().copy()
+        out["dlog_mu_sel"] = torch.autograd.grad(log_mu, th)[0].numpy().copy()
+    return out
+
+
 def tables(theta, wa=None):
     """theta-dependent tables (for unit-level parity of the prologue kernels)."""
     with torch.no_grad():

@@ -95,6 +95,38 @@ def run_pop_cosmo_model(sites, data, R_unit=0.0, grad=True):
     return out
 
 
+FIXED_SITES = ("a", "b", "c", "mpisn", "dmbhmax", "sigma", "beta", "log_fpl", "lam", "dkappa", "zp")
+
+
+def run_pop_model(sites, data, R_unit=0.0):
+    """Execute the reference's fixed-cosmology `pop_model` (intensity_models.py:313-355) unmodified; data are the
+    source-frame arguments (m1s, qs, zs, pdraw, m1s_sel, qs_sel, zs_sel, pdraw_sel, Ndraw).  Also returns the
+    dVdzdt table the model built (:323-325) so that the other implementations can be fed the same numbers."""
+    im = load_reference()
+    import numpyro  # the shim
+
+    leaves = {k: torch.tensor(float(sites[k]), dtype=torch.float64, requires_grad=True) for k in FIXED_SITES}
+    vals = dict(leaves)
+    vals["R_unit"] = torch.tensor(float(R_unit), dtype=torch.float64)
+    with numpyro.Recorder(vals) as rec:
+        im.pop_model(*data)
+    nobs = np.asarray(data[0]).shape[0]
+    loglike, selfactor = rec.factors["loglike"], rec.factors["selfactor"]
+    log_mu_sel = -selfactor / nobs
+    lv = [leaves[k] for k in FIXED_SITES]
+    g1 = torch.autograd.grad(loglike, lv, retain_graph=True, allow_unused=True)
+    g2 = torch.autograd.grad(log_mu_sel, lv, allow_unused=True)
+    zinterp = np.expm1(np.linspace(np.log1p(0), np.log1p(100), 1024))
+    from astropy.cosmology import Planck18  # the shim
+    tab = 4 * np.pi * Planck18.differential_comoving_volume(zinterp).value / (1 + zinterp)
+    return {"loglike": float(loglike), "selfactor": float(selfactor), "log_mu_sel": float(log_mu_sel),
+            "neff_sel": float(rec.deterministic["neff_sel"]), "neff": rec.deterministic["neff"].detach().numpy().copy(),
+            "R": float(rec.deterministic["R"]),
+            "dloglike_dsite": np.array([0.0 if g is None else float(g) for g in g1]),
+            "dlog_mu_sel_dsite": np.array([0.0 if g is None else float(g) for g in g2]),
+            "dvdzdt_interp": tab}
+
+
 def reference_tables(sites):
     """Reference cosmology tables and PISN table at the given site values (no grad)."""
     im = load_reference()

@@ -229,3 +229,25 @@ def test_host_model_mirror_matches_reference_sites_and_curves(golden_dir):
             ref = g["ref_" + name][k]
             assert _close(r[name], ref, rtol=1e-9, floor=max(1e-300, float(np.max(np.abs(ref))) * 1e-6)), (k, name)
     model.close()
+
+
+def test_fixed_cosmology_mode_matches_reference_pop_model(golden_dir):
+    """BUMP_FLAG_FIXED_COSMO through the host mirror `pop_model(...)`: the golden is the unmodified reference
+    `pop_model` (intensity_models.py:313-355)."""
+    from bumpcosmology_b200 import intensity_models as im
+    g = np.load(os.path.join(golden_dir, "pop_fixed_small.npz"))
+    data = (g["m1s"], g["qs"], g["zs"], g["pdraw"], g["m1s_sel"], g["qs_sel"], g["zs_sel"], g["pdraw_sel"],
+            float(g["Ndraw"]))
+    model = im.pop_model(*data, dVdzdt_interp=g["dvdzdt_interp"])
+    assert tuple(str(s) for s in g["site_names"]) == im.FIXED_SITES[:11]
+    for k, th in enumerate(g["thetas"]):
+        sites = dict(a=th[3], b=th[4], c=th[5], mpisn=th[6], dmbhmax=th[7] - th[6], sigma=th[8], beta=th[10],
+                     log_fpl=np.log(th[9]), lam=th[11], dkappa=th[12] - th[11], zp=th[13], R_unit=-0.5)
+        r = model(sites)
+        assert _close(r["loglike"], g["ref_loglike"][k]) and _close(r["selfactor"], g["ref_selfactor"][k])
+        assert _close(r["neff_sel"], g["ref_neff_sel"][k]) and _close(r["neff"], g["ref_neff"][k])
+        assert _close(r["R"], g["ref_R"][k])
+        scale = max(1.0, float(np.max(np.abs(g["ref_dloglike_dsite"][k]))))
+        assert _close(r["dloglike_dsite"], g["ref_dloglike_dsite"][k], floor=scale)
+        assert _close(r["dselfactor_dsite"], -r["nobs"] * g["ref_dlog_mu_sel_dsite"][k], floor=float(r["nobs"]))
+    model.close()

@@ -98,3 +98,21 @@ def test_gradient_vs_finite_differences(golden_dir):
         tm[i] -= eps
         fd = (bo.evaluate(tp, data, grad=False)["logl"] - bo.evaluate(tm, data, grad=False)["logl"]) / (2 * eps)
         assert abs(fd - r["dlogl"][i]) <= 2e-6 * max(1.0, abs(fd)), (i, fd, r["dlogl"][i])
+
+
+def test_fixed_cosmology_oracle_matches_reference_pop_model(golden_dir):
+    """oracle.evaluate_fixed against the golden minted from the unmodified reference `pop_model`
+    (intensity_models.py:313-355)."""
+    g = np.load(os.path.join(golden_dir, "pop_fixed_small.npz"))
+    data = (g["m1s"], g["qs"], g["zs"], g["pdraw"], g["m1s_sel"], g["qs_sel"], g["zs_sel"], g["pdraw_sel"],
+            float(g["Ndraw"]))
+    for k, th in enumerate(g["thetas"]):
+        r = bo.evaluate_fixed(th, data, g["dvdzdt_interp"])
+        assert _close(r["loglike"], g["ref_loglike"][k]) and _close(r["log_mu_sel"], g["ref_log_mu_sel"][k])
+        assert _close(r["neff_sel"], g["ref_neff_sel"][k], rtol=1e-10) and _close(r["neff"], g["ref_neff"][k], rtol=1e-10)
+        gs = bo.grad_sites_from_theta(r["dloglike"], th)[3:]
+        gm = bo.grad_sites_from_theta(r["dlog_mu_sel"], th)[3:]
+        scale = max(1.0, float(np.max(np.abs(g["ref_dloglike_dsite"][k]))))
+        assert _close(gs, g["ref_dloglike_dsite"][k], rtol=1e-10, floor=scale)
+        assert _close(gm, g["ref_dlog_mu_sel_dsite"][k], rtol=1e-10)
+        assert np.all(r["dloglike"][:3] == 0) and np.all(r["dlog_mu_sel"][:3] == 0)
