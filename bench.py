@@ -29,6 +29,10 @@ METRIC = "hyperlikelihood logL+grad evals/sec (O5 mock)"
 UNIT = "evals/s"
 ALGO_BYTES_PER_SAMPLE = 32           # m1_det, q, d_L, pdraw as fp64
 ALGO_FP64_INST_PER_SAMPLE = 700      # forward + 14-parameter gradient, FP64-pipe instructions
+# Measured with ncu on the same command (profiles/r01_o5_stream_kernel_opmix.txt / _ncu.txt): FP64-pipe warp
+# instructions the streaming kernel actually executes per 32 samples, and DRAM bytes it reads per sample.
+EXEC_FP64_INST_PER_SAMPLE = 266.0
+DRAM_BYTES_PER_SAMPLE = 56.1
 
 
 def measured_peaks():
@@ -161,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default=os.environ.get("BUMP_BENCH_WORKLOAD", "o5"))
-    ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "torch"), choices=("torch", "nccl"))
+    ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "nccl"), choices=("torch", "nccl"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -253,11 +257,15 @@ def main():
     pk = fp64_peak(local_rank)
     fp64 = None
     if "dfma_per_s" in pk:
-        inst = ALGO_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
+        inst = EXEC_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
+        algo = ALGO_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
         fp64 = {"bound": "fp64 pipe", "achieved": inst, "peak": pk["dfma_per_s"], "unit": "fp64 inst/s",
                 "frac": inst / pk["dfma_per_s"], "peak_fp64_tflops": pk["fp64_tflops"],
-                "note": "algorithmic 700 FP64-pipe instructions per sample (SURVEY.md 8d) x samples / kernel time, "
-                        "over the DFMA issue rate measured by bump_peak in this run"}
+                "inst_per_sample_executed": EXEC_FP64_INST_PER_SAMPLE,
+                "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE, "algorithmic_frac": algo / pk["dfma_per_s"],
+                "note": "frac = FP64-pipe instructions the kernel executes (ncu, profiles/) x samples / kernel time, "
+                        "over the DFMA issue rate measured by bump_peak in this run; algorithmic_frac uses SURVEY.md "
+                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 2.6x fewer"}
     value = K / (ms_total * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -277,7 +285,10 @@ def main():
         "gpu_launches": K * local.launches_per_eval,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "kernel": "stream_kernel",
+                     "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_SAMPLE * n_local,
+                     "traffic_note": "dram__bytes_read+write of one launch from ncu --set full (profiles/), per sample "
+                                     "x this rank's samples: 7 resident fp64 columns incl. hoisted logs",
+                     "kernel": "stream_kernel",
                      "kernel_ms": ker_ms, "peak_source": peak_src,
                      "note": "algorithmic 32 B/sample; the fp64 path is FP64-pipe bound, see fp64_pipe"},
         "fp64_pipe": fp64,

@@ -134,10 +134,10 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
 // Fixed-cosmology variant (the reference's `pop_model`, intensity_models.py:313-355): the sample carries source-frame
 // (m1, q) and log1p(z) directly, `lpd` = log pdraw - log dVdzdt(z) was folded at upload, and there is no d_L
 // inversion, no Jacobian and no cosmological gradient.
-template <bool WA>
+template <bool WA, class Mid>
 __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
                                                   const double lq, const double l1q, const double lpd,
-                                                  const double* __restrict__ s_blob, ThreadAcc& A) {
+                                                  const double* __restrict__ s_blob, ThreadAcc& A, Mid&& mid) {
     const double* __restrict__ expt = s_blob + OFF_EXPT;
     const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
     double m2 = q * m1;
@@ -148,6 +148,7 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
     }
     const double pair = lm1 + l1q;
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM], L, -lpd);   // :332 (no (1+z)^-2 Jacobian here)
+    mid();
     if (valid && lin - A.m > RESCALE_GAP) {
         const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
         A.a[0] *= s;
@@ -177,10 +178,13 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
     A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
 }
 
-template <bool WA>
+// `mid()` runs once every input of the sample has been consumed (used by the caller to issue the next loads there:
+// issuing them earlier makes the first use of THIS sample's inputs wait on a scoreboard slot shared with the fresh
+// loads, i.e. on a full L2 round trip).
+template <bool WA, class Mid>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
-                                            const double* __restrict__ s_blob, ThreadAcc& A) {
+                                            const double* __restrict__ s_blob, ThreadAcc& A, Mid&& mid) {
     const double* __restrict__ expt = s_blob + OFF_EXPT;
     const double2* __restrict__ cos = reinterpret_cast<const double2*>(s_blob + OFF_COS);
     const double* __restrict__ ctan = s_blob + OFF_CTAN;
@@ -188,13 +192,14 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
 
     // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
-    // bucket table keyed by the top bits of x gives a lower bound of the bin; walk up to the exact one.
+    // bucket table keyed by the top bits of x gives a lower bound of the bin; walk up to the exact one (a bucket
+    // is narrower than any bin, so this is at most one step; measured faster than a branch-free two-record select).
     int j = (__double2hiint(x) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
     j = min(max(j, 0), SRCH_N - 1);
     int b = srch[j];
     while (b < NZ - 2 && x >= cos[CR_DL * NZ + b + 1].x) ++b;
-    const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     const double2 rdl = cos[CR_DL * NZ + b];
+    const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     double t = (x - rdl.x) * rdl.y;
     const double idl = beyond ? 0.0 : rdl.y;
     t = beyond ? 1.0 : t;
@@ -223,6 +228,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     // ---- everything that is linear in precomputed logs: beta log(m1+m2) + log m1 + (lam-2) log1p(z) - log pdraw
     const double pair = lm1 + l1q;                  // log(m1+m2); the -beta log(60) is in the constant
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM2], L, -lpd);
+    mid();
     if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
         const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
         A.a[0] *= s;
@@ -376,24 +382,28 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     Half hx = load_half(p0, pitch, lane < count);
     for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32, pitch, 32 + lane < count);
-        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
-        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A);
-        // ---- advance to the next group and issue its x half; pull the group after it towards L2
+        auto nothing = [] {};
+        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A, nothing);
+        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A, nothing);
+        // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
+        // consumed), and the group after it is pulled towards L2
         int e_next = e, k_next = k + 1;
         if (k_next == ((e < wk.nobs) ? g_evt : n_groups - n_evt_groups)) {
             k_next = 0;
             e_next = e + 1;
         }
         const bool more = g + 1 < g1;
-        if (more) {
-            locate(e_next, k_next, p0, pitch, count);
-            hx = load_half(p0, pitch, lane < count);
-            const double* pf = p0 - lane + GROUP + (lane & 3) * 16;   // 4 lines of 128 B per column
+        auto next_loads = [&] {
+            if (more) {
+                locate(e_next, k_next, p0, pitch, count);
+                hx = load_half(p0, pitch, lane < count);
+                const double* pf = p0 - lane + GROUP + (lane & 3) * 16;   // 4 lines of 128 B per column
 #pragma unroll
-            for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
-        }
-        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
-        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A);
+                for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
+            }
+        };
+        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A, next_loads);
+        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A, next_loads);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);

@@ -214,7 +214,7 @@ class ShardedHyperlikelihood:
                'nccl'  : ncclAllGather issued by the library inside its CUDA graph (bump_comm_attach)
     """
 
-    def __init__(self, data, device=None, wa=False, exchange="torch", group=None):
+    def __init__(self, data, device=None, wa=False, exchange="nccl", group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
