@@ -31,7 +31,7 @@ ALGO_BYTES_PER_SAMPLE = 32           # m1_det, q, d_L, pdraw as 
 ALGO_FP64_INST_PER_SAMPLE = 700      # forward + 14-parameter gradient, FP64-pipe instructions
 # Measured with ncu on the same command (profiles/r01_o5_stream_kernel_opmix.txt / _ncu.txt): FP64-pipe warp
 # instructions the streaming kernel actually executes per 32 samples, and DRAM bytes it reads per sample.
-EXEC_FP64_INST_PER_SAMPLE = 266.0
+EXEC_FP64_INST_PER_SAMPLE = 256.5
 DRAM_BYTES_PER_SAMPLE = 56.1
 
 
