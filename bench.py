@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default=os.environ.get("BUMP_BENCH_WORKLOAD", "o5"))
-    ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "nccl"), choices=("torch", "nccl"))
+    ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "p2p"), choices=("torch", "nccl", "p2p"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -210,6 +210,18 @@ def main():
         torch.cuda.synchronize()
         ms_total, _ = local.time_evals(THETA_DEFAULT, K)
         torch.cuda.synchronize()
+    elif like.exchange in ("nccl", "p2p"):
+        # the exchange is part of the library's CUDA graph: time K graph replays with events on the context stream
+        like(THETA_DEFAULT)
+        local.time_evals(THETA_DEFAULT, W)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms_local, _ = local.time_evals(THETA_DEFAULT, K)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
     else:
         like(THETA_DEFAULT)
         for _ in range(W):
@@ -273,7 +285,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections",
                    "elements": cat.n_elements, "sharding": f"events and injections over {world} rank(s)",
-                   "exchange": args.exchange if world > 1 else "none",
+                   "exchange": getattr(like, "exchange", "none") if world > 1 else "none",
                    "l2": "per-rank resident columns %.2f GB > 126 MB L2" % (56 * n_local / 1e9)
                          if 56 * n_local > 2.5e8 else "columns fit in L2 (NUTS re-reads the same data)",
                    "plan": local.plan(), "catalog_gen_s": round(gen_s, 1), "upload_s": round(upload_s, 2)},

@@ -39,6 +39,9 @@ SIGNATURES = {
     "bump_finalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bump_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "bump_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "bump_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bump_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "bump_p2p_detach": (C.c_int, [C.c_void_p]),
     "bump_debug_tables": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64]),
     "bump_time_evals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bump_launches_per_eval": (C.c_int, [C.c_void_p]),

@@ -100,6 +100,51 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
     out[OUT_NSEL] = nsel;
 }
 
+// ---- fused exchange over peer memory (NVLink): every rank owns a mailbox that all peers can write.
+// mail[parity][rank][PARTIAL_LEN] receives rank's partial of the evaluation with that parity, flag[parity][rank] its
+// epoch.  The last block of the epilogue pushes this rank's partial into every mailbox (its own included), publishes
+// the epoch, waits until its own mailbox holds the current epoch from every rank, and finalizes — no NCCL call, no
+// extra launch.  Two parities: a rank can run at most one evaluation ahead of the slowest peer (it needs that peer's
+// current partial to finish), so the buffer it overwrites is never still being read.
+constexpr int P2P_MAX_RANKS = 16;
+struct Mailbox {
+    double mail[2][P2P_MAX_RANKS][PARTIAL_LEN];
+    unsigned long long flag[2][P2P_MAX_RANKS];
+};
+struct Peers {
+    Mailbox* box[P2P_MAX_RANKS];   // box[r] = rank r's mailbox as mapped into this process (box[rank] = local)
+    int nranks, rank;
+};
+
+// Called by all threads of ONE block.  Returns false on timeout (a peer never arrived).
+__device__ inline bool p2p_exchange(const Peers& peers, const double* __restrict__ partial,
+                                    unsigned long long* __restrict__ epoch_counter) {
+    __shared__ int s_ok;
+    const int tid = threadIdx.x;
+    const unsigned long long epoch = *epoch_counter + 1ull;
+    const int par = (int)(epoch & 1ull);
+    if (tid == 0) s_ok = 1;
+    for (int r = 0; r < peers.nranks; ++r)
+        for (int k = tid; k < PARTIAL_LEN; k += blockDim.x) peers.box[r]->mail[par][peers.rank][k] = partial[k];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < peers.nranks) {
+        *reinterpret_cast<volatile unsigned long long*>(&peers.box[tid]->flag[par][peers.rank]) = epoch;
+        const volatile unsigned long long* mine = &peers.box[peers.rank]->flag[par][tid];
+        const long long t0 = clock64();
+        while (*mine != epoch) {
+            if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer is gone; fail instead of hanging the GPU
+                s_ok = 0;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *epoch_counter = epoch;
+    return s_ok != 0;
+}
+
 __global__ void finalize_kernel(const double* __restrict__ partials, const int nranks, double* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) finalize_merge(partials, nranks, out);
 }
@@ -157,7 +202,8 @@ __global__ void __launch_bounds__(EPI_THREADS)
 epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off, const Work wk, const double nsel,
                 const int lpe /* lanes per event: power of two <= 32 */, const double* __restrict__ blob,
                 double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
-                double* __restrict__ partial, double* __restrict__ out_header) {
+                double* __restrict__ partial, double* __restrict__ out_header, const Peers* __restrict__ peers,
+                unsigned long long* __restrict__ epoch_counter) {
     __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
     __shared__ double s_max;
     __shared__ bool is_last;
@@ -296,7 +342,17 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     if (out_header) {
         __threadfence();
         __syncthreads();
-        if (tid == 0) finalize_merge(partial, 1, out_header);
+        if (peers) {   // multi-rank, fused exchange over peer memory
+            const bool ok = p2p_exchange(*peers, partial, epoch_counter);
+            if (tid == 0) {
+                const int par = (int)(*epoch_counter & 1ull);
+                finalize_merge(&peers->box[peers->rank]->mail[par][0][0], peers->nranks, out_header);
+                if (!ok)
+                    for (int k = 0; k < OUT_NVALID_EVT; ++k) out_header[k] = NAN;
+            }
+        } else if (tid == 0) {
+            finalize_merge(partial, 1, out_header);
+        }
     }
 }
 

@@ -202,6 +202,11 @@ struct bump_ctx {
     // communicator
     void* comm = nullptr;
     int nranks = 1, rank = 0;
+    // fused exchange over peer memory
+    Mailbox* d_mailbox = nullptr;            // this rank's mailbox (cudaMalloc: IPC-exportable)
+    Peers* d_peers = nullptr;                // device copy of the peer table (null: not attached)
+    unsigned long long* d_epoch = nullptr;
+    void* peer_ptr[P2P_MAX_RANKS] = {};      // mappings opened with cudaIpcOpenMemHandle
 };
 
 namespace {
@@ -360,14 +365,14 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
     epilogue_kernel<<<nb_evt + 1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->lpe,
                                                        c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
-                                                       fused_out);
+                                                       fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch);
     CK(cudaGetLastError());
     return BUMP_OK;
 }
 
 int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStream_t s, cudaEvent_t k0 = nullptr,
                 cudaEvent_t k1 = nullptr) {
-    // single rank: the epilogue's last block finalizes in place (3 launches per evaluation)
+    // single rank, or peer-memory exchange: the epilogue's last block finalizes in place (4 launches per evaluation)
     if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev))
         return r;
     if (c->comm) {
@@ -493,6 +498,11 @@ void bump_ctx_destroy(bump_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_plan(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+    cudaFree(c->d_mailbox);
+    cudaFree(c->d_peers);
+    cudaFree(c->d_epoch);
     cudaFree(c->evt.base);
     cudaFree(c->sel.base);
     cudaFree(c->d_theta);
@@ -614,6 +624,66 @@ int bump_comm_attach(bump_ctx* c, const void* id128, int nranks, int rank) {
     c->rank = rank;
     cudaFree(c->d_gather);
     CK(cudaMalloc(&c->d_gather, sizeof(double) * PARTIAL_LEN * nranks));
+    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    return BUMP_OK;
+}
+
+int bump_p2p_export(bump_ctx* c, void* handle64) {
+    if (!c || !handle64) return fail(BUMP_E_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (int r = set_device(c)) return r;
+    if (!c->d_mailbox) {
+        CK(cudaMalloc(&c->d_mailbox, sizeof(Mailbox)));
+        CK(cudaMemset(c->d_mailbox, 0, sizeof(Mailbox)));
+        CK(cudaMalloc(&c->d_epoch, sizeof(unsigned long long)));
+        CK(cudaMemset(c->d_epoch, 0, sizeof(unsigned long long)));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->d_mailbox));
+    memcpy(handle64, &h, sizeof(h));
+    return BUMP_OK;
+}
+
+int bump_p2p_attach(bump_ctx* c, const void* handles, int nranks, int rank) {
+    if (!c || !handles || nranks < 1 || nranks > P2P_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(BUMP_E_INVALID, "bad p2p arguments (at most 16 ranks)");
+    if (!c->d_mailbox) return fail(BUMP_E_INVALID, "call bump_p2p_export first");
+    if (c->comm) return fail(BUMP_E_INVALID, "an NCCL communicator is already attached");
+    if (int r = set_device(c)) return r;
+    Peers p;
+    memset(&p, 0, sizeof(p));
+    p.nranks = nranks;
+    p.rank = rank;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            p.box[r] = c->d_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * r, sizeof(h));
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_ptr[r] = ptr;
+        p.box[r] = static_cast<Mailbox*>(ptr);
+    }
+    if (!c->d_peers) CK(cudaMalloc(&c->d_peers, sizeof(Peers)));
+    CK(cudaMemcpy(c->d_peers, &p, sizeof(p), cudaMemcpyHostToDevice));
+    c->nranks = nranks;
+    c->rank = rank;
+    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    return BUMP_OK;
+}
+
+int bump_p2p_detach(bump_ctx* c) {
+    if (!c) return fail(BUMP_E_INVALID, "null context");
+    if (int r = set_device(c)) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]), c->peer_ptr[r] = nullptr;
+    cudaFree(c->d_peers), c->d_peers = nullptr;
+    c->nranks = 1;
+    c->rank = 0;
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
     return BUMP_OK;
 }

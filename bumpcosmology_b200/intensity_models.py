@@ -32,7 +32,7 @@ class PopCosmoModel:
     """The reference model bound to its data (what numpyro holds after `mcmc.run(key, *data)`)."""
 
     def __init__(self, m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw, device=0,
-                 distributed=False, exchange="nccl"):
+                 distributed=False, exchange="p2p"):
         data = (m1s_det, qs, dls, pdraw, m1s_det_sel, qs_sel, dls_sel, pdraw_sel, Ndraw)
         if distributed:
             self.like = ShardedHyperlikelihood(data, device=device, exchange=exchange)

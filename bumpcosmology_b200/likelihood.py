@@ -212,9 +212,11 @@ class ShardedHyperlikelihood:
 
     exchange = 'torch' : torch.distributed.all_gather_into_tensor between the partial and finalize launches
                'nccl'  : ncclAllGather issued by the library inside its CUDA graph (bump_comm_attach)
+               'p2p'   : no collective call at all — the epilogue kernel's last block writes the partial into every
+                         peer's mailbox over NVLink (cudaIpc-mapped peer memory) and merges (bump_p2p_attach)
     """
 
-    def __init__(self, data, device=None, wa=False, exchange="nccl", group=None):
+    def __init__(self, data, device=None, wa=False, exchange="p2p", group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -231,6 +233,23 @@ class ShardedHyperlikelihood:
         self._gathered = torch.zeros(self.world * _lib.PARTIAL_LEN, dtype=torch.float64, device=dev)
         self._out = torch.zeros(_lib.OUT_HEADER + self.local.nobs, dtype=torch.float64, device=dev)
         self._out_h = torch.zeros(_lib.OUT_HEADER + self.local.nobs, dtype=torch.float64).pin_memory()
+        if exchange == "p2p":
+            # peer mailboxes need CUDA IPC between the ranks' processes; if any rank cannot map its peers, every rank
+            # falls back to the in-library NCCL all-gather
+            lib, ctx = self.local.lib, self.local._ctx
+            raw = (C.c_char * 64)()
+            ok = lib.bump_p2p_export(ctx, raw) == 0
+            mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone().to(dev)
+            allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            hb = allh.cpu().numpy().tobytes()
+            buf = (C.c_char * len(hb)).from_buffer_copy(hb)
+            ok = ok and lib.bump_p2p_attach(ctx, buf, self.world, self.rank) == 0
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                lib.bump_p2p_detach(ctx)
+                self.exchange = exchange = "nccl"
         if exchange == "nccl":
             idbuf = torch.zeros(128, dtype=torch.uint8)
             if self.rank == 0:
@@ -245,7 +264,7 @@ class ShardedHyperlikelihood:
         """Enqueue one evaluation (theta already in self._theta) on the current torch stream."""
         torch = self.torch
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        if self.exchange == "nccl":
+        if self.exchange in ("nccl", "p2p"):
             self.local.eval_device(self._theta.data_ptr(), self._out.data_ptr(), s)
         else:
             self.local.partial_device(self._theta.data_ptr(), self._partial.data_ptr(),
@@ -254,6 +273,8 @@ class ShardedHyperlikelihood:
             self.local.finalize_device(self._gathered.data_ptr(), self.world, self._out.data_ptr(), s)
 
     def __call__(self, theta):
+        if self.exchange in ("nccl", "p2p"):   # the exchange lives inside the library's CUDA graph
+            return self.local(theta)
         th = np.asarray(theta, dtype=np.float64).ravel()
         self._theta_h[:self.ntheta] = self.torch.from_numpy(th)
         self._theta.copy_(self._theta_h, non_blocking=True)

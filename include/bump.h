@@ -115,6 +115,17 @@ int bump_finalize_device(bump_ctx* ctx, const double* partials_dev, int nranks, 
 int bump_nccl_unique_id(void* id128);
 int bump_comm_attach(bump_ctx* ctx, const void* id128, int nranks, int rank);
 
+/* Multi-GPU, fused exchange over peer memory (NVLink/NVSwitch, ranks = processes of ONE node, one GPU each): the last
+ * block of the epilogue kernel stores this rank's partial straight into every peer's mailbox, publishes an epoch
+ * flag, waits for the peers' flags and merges — no NCCL call and no extra launch on the evaluation path.
+ * bump_p2p_export writes this rank's 64-byte cudaIpcMemHandle_t; the host all-gathers the handles (any transport)
+ * and passes the [nranks][64] array to bump_p2p_attach.  At most 16 ranks.  Every rank must then call bump_eval /
+ * bump_eval_device the same number of times (it is a collective); a peer that never arrives makes the others return
+ * NaN after ~10 s instead of hanging the GPU. */
+int bump_p2p_export(bump_ctx* ctx, void* handle64);
+int bump_p2p_attach(bump_ctx* ctx, const void* handles, int nranks, int rank);
+int bump_p2p_detach(bump_ctx* ctx);   /* back to a single-rank context (e.g. to fall back to bump_comm_attach) */
+
 /* Introspection for unit-level parity tests of the prologue kernels (F1-F3 of SURVEY.md section 2.2):
  * copies the theta-dependent tables of the last evaluation to the host.
  *   which = 0: cosmology knots  [4][1024]: zinterp, dlinterp, ddlinterp, dvcinterp      (intensity_models.py:230-235)

@@ -43,7 +43,7 @@ def _worker(rank, world, port, out_dir, exchange):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ("torch", "nccl"))
+@pytest.mark.parametrize("exchange", ("torch", "nccl", "p2p"))
 def test_two_ranks_match_single_gpu(tmp_path, exchange):
     import torch
     import torch.multiprocessing as mp
