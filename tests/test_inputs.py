@@ -20,7 +20,7 @@ def test_fiducial_cosmology_agrees_with_the_catalog_generator():
     f = catalogs._FiducialCosmology()
     z = np.linspace(0.01, 3.0, 50)
     # catalogs.py uses the reference's c/H100 = 2.99792 constant; astropy's is 2.99792458
-    assert np.allclose(c.luminosity_distance(z), np.interp(z, f.z, f.dl), rtol=3e-6)
+    assert np.allclose(c.luminosity_distance(z), np.interp(z, f.z, f.dl), rtol=2e-5)   # 4096-point table interpolation
 
 
 def test_model_arguments_roundtrip():
