@@ -156,17 +156,19 @@ def test_edge_cases(hl):
     like.close()
 
 
-def test_partials_merge_equals_single_rank(hl):
-    """Emulate 3 ranks on one GPU: shard, evaluate partials, merge on the host (same code as the device
-    finalize) -> equals the unsharded evaluation to 1e-12."""
+@pytest.mark.parametrize("name,world", (("small", 3), ("tiny", 8)))
+def test_partials_merge_equals_single_rank(hl, name, world):
+    """Emulate several ranks on one GPU: shard, evaluate partials, merge on the host (same code as the device
+    finalize) -> equals the unsharded evaluation to 1e-12.  ("tiny", 8): 5 events over 8 ranks leaves ranks with
+    no event at all."""
     from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
     from bumpcosmology_b200.likelihood import merge_partials, shard_catalog, unpack_header
-    cat = make_catalog("small", seed=17)
+    cat = make_catalog(name, seed=17)
     full = hl(*cat.as_args())
     r = full(THETA_DEFAULT)
     parts, neffs = [], []
-    for rank in range(3):
-        sh = hl(*shard_catalog(cat.as_args(), rank, 3))
+    for rank in range(world):
+        sh = hl(*shard_catalog(cat.as_args(), rank, world))
         p, ne = sh.partial(THETA_DEFAULT)
         parts.append(p)
         neffs.append(ne)
