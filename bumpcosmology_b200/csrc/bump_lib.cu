@@ -345,8 +345,10 @@ EvalConsts consts_of(const bump_ctx* c) {
 // The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr) {
-    tables_kernel<<<NM + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_ticket + 2, c->use_wa ? 1 : 0);
-    records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c));
+    tables_kernel<<<NM + COS_CHUNKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_ticket + 2, c->use_wa ? 1 : 0,
+                                                          c->d_aux + AUX_DOUBLES, c->d_ticket + 4);
+    records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c),
+                                                          c->d_ticket + 4);
     CK(cudaMemcpyToSymbolAsync(K_SC, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL, 0, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0) {
@@ -475,12 +477,13 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaMemset(c->d_theta, 0, sizeof(double) * NTHETA_MAX));
-    CK(cudaMalloc(&c->d_aux, sizeof(double) * AUX_DOUBLES));
+    CK(cudaMalloc(&c->d_aux, sizeof(double) * (AUX_DOUBLES + AUX_CHAIN_DOUBLES)));
     CK(cudaMalloc(&c->d_blob, BLOB_BYTES));
     CK(cudaMemset(c->d_blob, 0, BLOB_BYTES));
     CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
-    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));   // [0] prologue ticket, [1] epilogue ticket, [2] bad flag
-    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
+    // [0] unused, [1] epilogue ticket, [2] bad-theta flag, [3] bad-input flag, [4..7] cosmology scan-chain flags
+    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8));
+    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 8));
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));

@@ -121,13 +121,21 @@ __device__ void pisn_row(const double* __restrict__ th, int i, double* __restric
 }
 
 // ---------------------------------------------------------------- cosmology tables (Dual<3>: Om, w, wa)
-__device__ void cosmology_tables(const double* __restrict__ th, int use_wa, double* __restrict__ aux, double* sm) {
+// The 1024 knots are split over COS_CHUNKS blocks (one knot per thread): the single-block version was the critical
+// path of the whole prologue (13 us against 9 us for all 256 PISN rows).  The cumulative trapezoid crosses chunks
+// through a small chain in global memory (totals + flag per chunk); the chunks are the first blocks of the grid, so
+// they are resident together and a later chunk can safely wait for an earlier one.
+constexpr int COS_CHUNKS = 4;
+constexpr int AUX_CHAIN_DOUBLES = COS_CHUNKS * 4;
+
+__device__ void cosmology_tables(const double* __restrict__ th, int use_wa, double* __restrict__ aux, double* sm,
+                                 const int chunk, double* __restrict__ chain, unsigned int* __restrict__ chain_flag) {
     typedef Dual<3> D;
-    const int tid = threadIdx.x;
+    const int tid = chunk * PRO_THREADS + threadIdx.x;   // global knot-thread index
     const double h = th[T_H];
     D Om = D::var(th[T_OM], 0), w = D::var(th[T_W], 1), wa = D::var(use_wa ? th[T_WA] : 0.0, 2);
     const double dH = C_H100_GPC / h;   // :239
-    constexpr int PER = NZ / PRO_THREADS;  // 4 knots per thread
+    constexpr int PER = NZ / (PRO_THREADS * COS_CHUNKS);  // 1 knot per thread (+ its right neighbour, recomputed)
     double z[PER + 1];
     D iE[PER + 1];
 #pragma unroll
@@ -151,7 +159,7 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
         inc[q] = (k < NZ - 1) ? (0.5 * (z[q + 1] - z[q])) * (iE[q] + iE[q + 1]) : D(0.0);
         tot = tot + inc[q];
     }
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double sc[4] = {tot.v, tot.d[0], tot.d[1], tot.d[2]};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -166,7 +174,32 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
         for (int c = 0; c < 4; ++c) sm[warp * 4 + c] = sc[c];
     }
     __syncthreads();
-    double base[4] = {0, 0, 0, 0};
+    // chain across chunks: publish this chunk's total, then wait for the earlier chunks
+    if (threadIdx.x == PRO_THREADS - 1) {
+        // sc[] of the last thread of the last warp is that warp's inclusive total; add the earlier warps
+        double t4[4] = {sc[0], sc[1], sc[2], sc[3]};
+        for (int ww = 0; ww < PRO_THREADS / 32 - 1; ++ww) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t4[c] += sm[ww * 4 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chain[chunk * 4 + c] = t4[c];
+        __threadfence();
+        atomicExch(chain_flag + chunk, 1u);
+    }
+    if (threadIdx.x == 0) {
+        double p4[4] = {0, 0, 0, 0};
+        for (int cc = 0; cc < chunk; ++cc) {
+            while (atomicAdd(chain_flag + cc, 0u) == 0u) {}
+            __threadfence();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p4[c] += __ldcg(chain + cc * 4 + c);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm[64 + c] = p4[c];
+    }
+    __syncthreads();
+    double base[4] = {sm[64], sm[65], sm[66], sm[67]};
     for (int ww = 0; ww < warp; ++ww) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) base[c] += sm[ww * 4 + c];
@@ -282,27 +315,27 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
 }
 
 // ---------------------------------------------------------------- kernel 1: raw tables with tangents
-//   blocks 0..NM-1 : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
-//   block  NM      : flat wCDM distance tables        (intensity_models.py:229-235 + utils.py:3-8 cumtrapz)
+//   blocks 0..3        : flat wCDM distance tables, 256 knots each (intensity_models.py:229-235 + utils.py:3-8)
+//   blocks 4..4+NM-1   : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
 __global__ void __launch_bounds__(PRO_THREADS)
 tables_kernel(const double* __restrict__ theta, double* __restrict__ aux, unsigned int* __restrict__ flags,
-              const int use_wa) {
+              const int use_wa, double* __restrict__ chain, unsigned int* __restrict__ chain_flag) {
     __shared__ double sm[9 * NM + 64];
     __shared__ double th[NTHETA_MAX];
     if (threadIdx.x < NTHETA_MAX) th[threadIdx.x] = (threadIdx.x < NTHETA || use_wa) ? theta[threadIdx.x] : 0.0;
     __syncthreads();
-    if (blockIdx.x < NM) pisn_row(th, blockIdx.x, aux, sm);
-    else cosmology_tables(th, use_wa, aux, sm);
+    const bool is_cos = blockIdx.x < COS_CHUNKS;    // cosmology chunks first: they are the longer chains
+    const int row = (int)blockIdx.x - COS_CHUNKS;
+    if (!is_cos) pisn_row(th, row, aux, sm);
+    else cosmology_tables(th, use_wa, aux, sm, blockIdx.x, chain, chain_flag);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     int bad = 0;
     __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
-    if (blockIdx.x < NM) {
-        if (threadIdx.x < 6) bad = !isfinite(__ldcg(aux + AUX_G + threadIdx.x * NM + blockIdx.x));
+    if (!is_cos) {
+        if (threadIdx.x < 6) bad = !isfinite(__ldcg(aux + AUX_G + threadIdx.x * NM + row));
     } else {
-        for (int q = 0; q < NZ / PRO_THREADS; ++q) {
-            const int k = threadIdx.x * (NZ / PRO_THREADS) + q;
-            for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));
-        }
+        const int k = blockIdx.x * PRO_THREADS + threadIdx.x;
+        for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1u);
@@ -316,7 +349,7 @@ constexpr int REC_BLOCKS = (REC_ITEMS + PRO_THREADS - 1) / PRO_THREADS;   // + 1
 
 __global__ void __launch_bounds__(PRO_THREADS)
 records_kernel(const double* __restrict__ theta, const double* __restrict__ aux, double* __restrict__ blob,
-               unsigned int* __restrict__ flags, const EvalConsts ec) {
+               unsigned int* __restrict__ flags, const EvalConsts ec, unsigned int* __restrict__ chain_flag) {
     __shared__ double sm[6 * NM];
     if (blockIdx.x == REC_BLOCKS) {
         for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) sm[k] = aux[AUX_G + k];
@@ -327,6 +360,7 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
             build_scalars(th, aux, sm, ec, blob + OFF_SCAL);
             blob[OFF_SCAL + S_BAD] = (*flags != 0u) ? 1.0 : 0.0;
             *flags = 0u;
+            for (int cc = 0; cc < COS_CHUNKS; ++cc) chain_flag[cc] = 0u;   // re-arm the scan chain of tables_kernel
         }
         return;
     }
