@@ -253,7 +253,17 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    clock_note = None
+    if sampler is not None and len(sampler.lines) < 5:
+        # short timed regions (small catalogs) end before nvidia-smi delivers its first samples: keep the same load
+        # running, untimed, until a handful of samples exist
+        t_end = time.perf_counter() + 2.0
+        while len(sampler.lines) < 5 and time.perf_counter() < t_end:
+            local.time_evals(THETA_DEFAULT, 50) if world == 1 else time.sleep(0.05)
+        clock_note = "timed region shorter than the sampling period: sampled under the same load right after it"
     clocks = sampler.stop() if sampler else None
+    if clocks is not None and clock_note:
+        clocks["note"] = clock_note
     # ---- dominant kernel alone (events around each launch on its stream)
     _, ker_ms = local.time_evals(THETA_DEFAULT, max(3, min(K, 10)), kernel=True)
     ker_ms /= max(3, min(K, 10))

@@ -80,15 +80,14 @@ class PopCosmoModel:
     # ---- potential energy in unconstrained space, as numpyro's NUTS sees the model
     def potential(self, u):
         """U(u) = -[log prior(x(u)) + log|dx/du| + loglike + selfactor] and dU/du (15-dim, incl. R_unit)."""
-        x, dx, lj, dlj = priors.constrain(u)
-        lp, glp = priors.log_prior(x)
-        ev = self.evaluate(x)
+        x, dx, lpj, glp, dlj = priors.potential_terms(u)
+        ev = self.evaluate(np.array(x))
         logl = ev["loglike"] + ev["selfactor"]
-        if not (math.isfinite(logl) and math.isfinite(lp)):
+        if not (math.isfinite(logl) and math.isfinite(lpj)):
             return math.inf, np.zeros(priors.NSITES), ev
-        g = glp.copy()
+        g = np.array(glp)
         g[:14] += ev["dloglike_dsite"] + ev["dselfactor_dsite"]
-        return -(lp + lj + logl), -(g * dx + dlj), ev
+        return -(lpj + logl), -(g * np.array(dx) + np.array(dlj)), ev
 
     # ---- output-only curves (:403-406) from the tables the device built for this theta
     def diagnostics(self, theta, R):

@@ -141,6 +141,52 @@ def constrain(u):
     return x, dx, lj, dlj
 
 
+def potential_terms(u):
+    """One pass over the sites for NUTS: (x, dx/du, log prior + log|dx/du|, d/du of that sum's explicit part).
+
+    Equivalent to constrain() followed by log_prior(), fused and kept in plain Python floats (15 scalars: numpy
+    costs more than it saves here).  Returns (x list, dx list, logp_plus_logjac, glp list, dlj list) where the
+    gradient of the total with respect to u is glp*dx + dlj."""
+    xs, dxs, glps, dljs = [], [], [], []
+    total = 0.0
+    exp, log1p, log = math.exp, math.log1p, math.log
+    for s, ui in zip(SITES, u):
+        ui = float(ui)
+        lo, hi = s.lo, s.hi
+        if lo != -math.inf and hi != math.inf:
+            if ui >= 0:
+                e = exp(-ui)
+                sg = 1.0 / (1.0 + e)
+                lsig2 = -ui - 2.0 * log1p(e)
+            else:
+                e = exp(ui)
+                sg = e / (1.0 + e)
+                lsig2 = ui - 2.0 * log1p(e)
+            w = hi - lo
+            x = lo + w * sg
+            dx = w * sg * (1.0 - sg)
+            total += log(w) + lsig2
+            dlj = 1.0 - 2.0 * sg
+        elif lo != -math.inf:
+            e = exp(ui)
+            x, dx, dlj = lo + e, e, 1.0
+            total += ui
+        else:
+            x, dx, dlj = ui, 1.0, 0.0
+        if s.kind == "u":
+            total -= log(hi - lo)
+            glp = 0.0
+        else:
+            z = (x - s.a) / s.b
+            total += -0.5 * z * z - _LOG_SQRT_2PI - log(s.b) - (s.log_z if s.kind == "tn" else 0.0)
+            glp = -z / s.b
+        xs.append(x)
+        dxs.append(dx)
+        glps.append(glp)
+        dljs.append(dlj)
+    return xs, dxs, total, glps, dljs
+
+
 def unconstrain(x):
     return np.array([s.inverse(float(x[i])) for i, s in enumerate(SITES)])
 

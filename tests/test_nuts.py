@@ -85,3 +85,14 @@ def test_site_chain_rule_matches_oracle_helper():
     assert np.allclose(th, bo.theta_from_sites(s))
     g = rng.standard_normal(14)
     assert np.allclose(priors.grad_sites_from_theta(g, th), bo.grad_sites_from_theta(g, th))
+
+
+def test_fused_potential_terms_equal_constrain_plus_log_prior():
+    rng = np.random.default_rng(9)
+    for _ in range(100):
+        u = rng.uniform(-4, 4, priors.NSITES)
+        x, dx, lj, dlj = priors.constrain(u)
+        lp, g = priors.log_prior(x)
+        xs, dxs, tot, glp, dljs = priors.potential_terms(u)
+        assert np.allclose(x, xs, rtol=1e-14) and np.allclose(dx, dxs, rtol=1e-13)
+        assert abs(tot - (lp + lj)) < 1e-11 and np.allclose(g, glp, atol=1e-13) and np.allclose(dlj, dljs, atol=1e-14)
