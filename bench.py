@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("BUMP_BENCH_WORKLOAD", "o5"))
     ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "p2p"), choices=("torch", "nccl", "p2p"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wa", action="store_true",
+                    help="w0-wa (CPL) dark energy variant (BASELINE.json config 5): 15 parameters, the d_L(z) grid is "
+                         "rebuilt on the device every step by the cumulative-trapezoid tables kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -193,12 +196,16 @@ def main():
 
     cat, gen_s = workload_catalog(args.workload)
     thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(15, seed=5)])
+    if args.wa:   # append wa: 0.3 at the fiducial point, seeded uniform(-1, 1) elsewhere
+        wa_col = np.concatenate([[0.3], np.random.default_rng(11).uniform(-1, 1, len(thetas) - 1)])
+        thetas = np.hstack([thetas, wa_col[:, None]])
+    THETA_DEFAULT = thetas[0]
     t0 = time.time()
     if world > 1:
-        like = ShardedHyperlikelihood(cat.as_args(), device=local_rank, exchange=args.exchange)
+        like = ShardedHyperlikelihood(cat.as_args(), device=local_rank, exchange=args.exchange, wa=args.wa)
         local = like.local
     else:
-        like = local = Hyperlikelihood(*cat.as_args(), device=local_rank)
+        like = local = Hyperlikelihood(*cat.as_args(), device=local_rank, wa=args.wa)
     upload_s = time.time() - t0
     n_local = local.nobs * local.nsamp + local.nsel
     K, W = args.steps, args.warmup
@@ -293,7 +300,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections",
+        "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections"
+                               + (", w0-wa dark energy (15 parameters)" if args.wa else ""),
                    "elements": cat.n_elements, "sharding": f"events and injections over {world} rank(s)",
                    "exchange": getattr(like, "exchange", "none") if world > 1 else "none",
                    "l2": "per-rank resident columns %.2f GB > 126 MB L2" % (56 * n_local / 1e9)
@@ -316,7 +324,7 @@ def main():
         "fp64_pipe": fp64,
         "result_check": {"logl": res.logl, "neff_sel": res.neff_sel},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.wa:
         frac = min(1.0, 900_000 / cat.n_elements)
         v, sample, t_step, threads = cpu_baseline(cat, frac, frac, evals=8, warm=2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
