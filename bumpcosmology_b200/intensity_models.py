@@ -79,15 +79,47 @@ class PopCosmoModel:
 
     # ---- potential energy in unconstrained space, as numpyro's NUTS sees the model
     def potential(self, u):
-        """U(u) = -[log prior(x(u)) + log|dx/du| + loglike + selfactor] and dU/du (15-dim, incl. R_unit)."""
+        """U(u) = -[log prior(x(u)) + log|dx/du| + loglike + selfactor] and dU/du (15-dim, incl. R_unit).
+
+        This is the sampler's inner loop: one raw library call and plain-float host arithmetic.  The third return
+        value is a light record; `deterministics(record)` expands it to the site names of `evaluate`."""
         x, dx, lpj, glp, dlj = priors.potential_terms(u)
-        ev = self.evaluate(np.array(x))
-        logl = ev["loglike"] + ev["selfactor"]
+        h, Om, w, a, b, c, mpisn, dmbhmax, sigma, beta, log_fpl, lam, dkappa, zp, r_unit = x
+        fpl = math.exp(log_fpl)
+        theta = (h, Om, w, a, b, c, mpisn, mpisn + dmbhmax, sigma, fpl, beta, lam, lam + dkappa, zp)
+        out = self.like.raw(theta) if hasattr(self.like, "raw") else None
+        if out is None:   # sharded torch-exchange path: no raw entry point
+            ev = self.evaluate(np.array(x))
+            logl = ev["loglike"] + ev["selfactor"]
+            if not (math.isfinite(logl) and math.isfinite(lpj)):
+                return math.inf, np.zeros(priors.NSITES), ev
+            g = np.array(glp)
+            g[:14] += ev["dloglike_dsite"] + ev["dselfactor_dsite"]
+            return -(lpj + logl), -(g * np.array(dx) + np.array(dlj)), ev
+        self.n_evals += 1
+        nobs = out[36]
+        loglike, log_mu = out[0], out[1]
+        logl = loglike - nobs * log_mu
+        rec = (theta, r_unit, out[:40].copy(), out[40:].copy())
         if not (math.isfinite(logl) and math.isfinite(lpj)):
-            return math.inf, np.zeros(priors.NSITES), ev
-        g = np.array(glp)
-        g[:14] += ev["dloglike_dsite"] + ev["dselfactor_dsite"]
-        return -(lpj + logl), -(g * np.array(dx) + np.array(dlj)), ev
+            return math.inf, np.zeros(priors.NSITES), rec
+        gt = out[4:18] - nobs * out[19:33]            # d(loglike + selfactor)/d theta
+        g = [gt[0], gt[1], gt[2], gt[3], gt[4], gt[5], gt[6] + gt[7], gt[7], gt[8], gt[10], fpl * gt[9],
+             gt[11] + gt[12], gt[12], gt[13], 0.0]    # chain rule to the sites (priors.grad_sites_from_theta)
+        grad = np.array([-((g[i] + glp[i]) * dx[i] + dlj[i]) for i in range(15)])
+        return -(lpj + logl), grad, rec
+
+    @staticmethod
+    def deterministics(rec):
+        """Expand the light record of `potential` into the reference's deterministic / factor names."""
+        if isinstance(rec, dict):
+            return rec
+        theta, r_unit, hdr, neff = rec
+        nobs = hdr[36]
+        mu = math.exp(hdr[1]) if math.isfinite(hdr[1]) else float("nan")
+        return {"loglike": hdr[0], "selfactor": -nobs * hdr[1], "neff_sel": hdr[3], "neff": neff,
+                "R": nobs / mu + math.sqrt(nobs) / mu * r_unit, "mbhmax": theta[7], "fpl": theta[9],
+                "kappa": theta[12]}
 
     # ---- output-only curves (:403-406) from the tables the device built for this theta
     def diagnostics(self, theta, R):

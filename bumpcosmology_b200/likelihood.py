@@ -113,6 +113,7 @@ class Hyperlikelihood:
                                                    self.Ndraw))
         self._out = np.empty(int(self.lib.bump_out_len(self._ctx)), dtype=np.float64)
         self._theta = np.zeros(_lib.NTHETA_MAX, dtype=np.float64)
+        self._out_p, self._theta_p = _lib.as_dp(self._out), _lib.as_dp(self._theta)
 
     # -- lifetime
     def close(self):
@@ -139,6 +140,14 @@ class Hyperlikelihood:
         _lib.check(self.lib.bump_eval(self._ctx, _lib.as_dp(th), _lib.as_dp(self._out)))
         hdr = unpack_header(self._out, self.ntheta)
         return Evaluation(neff=self._out[_lib.OUT_HEADER:].copy(), **hdr)
+
+    def raw(self, theta):
+        """Same evaluation, no wrapping: returns the library's output vector (a view that the next call overwrites):
+        [0:40] = header (include/bump.h BUMP_OUT_*), [40:] = neff.  The sampler's inner loop uses this."""
+        th = self._theta
+        th[:self.ntheta] = theta
+        _lib.check(self.lib.bump_eval(self._ctx, self._theta_p, self._out_p))
+        return self._out
 
     # -- pieces for multi-rank drivers
     def partial(self, theta):
@@ -271,6 +280,9 @@ class ShardedHyperlikelihood:
                                       self._out.data_ptr() + 8 * _lib.OUT_HEADER, s)
             self.dist.all_gather_into_tensor(self._gathered, self._partial, group=self.group)
             self.local.finalize_device(self._gathered.data_ptr(), self.world, self._out.data_ptr(), s)
+
+    def raw(self, theta):
+        return self.local.raw(theta) if self.exchange in ("nccl", "p2p") else None
 
     def __call__(self, theta):
         if self.exchange in ("nccl", "p2p"):   # the exchange lives inside the library's CUDA graph

@@ -245,9 +245,10 @@ def run_chain(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
             out_x[j] = priors.constrain(u)[0]
             stats["accept"][j], stats["depth"][j], stats["n_leapfrog"][j] = acc, depth, nlf
             stats["diverging"][j], stats["potential"][j] = div, U
+            evd = model.deterministics(ev) if hasattr(model, "deterministics") else ev
             for name in ("loglike", "selfactor", "neff_sel", "R", "mbhmax", "fpl", "kappa"):
-                det[name].append(ev[name])
-            det["neff_min"].append(float(np.min(ev["neff"])) if len(ev["neff"]) else float("nan"))
+                det[name].append(evd[name])
+            det["neff_min"].append(float(np.min(evd["neff"])) if len(evd["neff"]) else float("nan"))
         if progress and (it + 1) % progress == 0:
             print(f"  chain seed {seed}: {it + 1}/{total} eps={eps:.4f} depth={depth} acc={acc:.2f}", flush=True)
     t_end = time.perf_counter()
@@ -257,13 +258,45 @@ def run_chain(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
 
 
 def run_mcmc(model, num_warmup=1000, num_samples=1000, num_chains=4, seed=1652819403, **kw):
-    """The reference's MCMC configuration (run_cosmo_fit.py:17-19,45-46); chains run one after another on the
-    same device-resident catalog."""
-    chains = [run_chain(model, num_warmup, num_samples, seed=seed + c, **kw) for c in range(num_chains)]
+    """The reference's MCMC configuration (run_cosmo_fit.py:17-19,45-46).
+
+    `model` is one bound model (chains run one after another on it) or a list of `num_chains` bound models, one per
+    chain, which then run concurrently in threads — the reference's chains are parallel too (numpyro pmaps them over
+    host devices, run_cosmo_fit.py:1-3).  The C call releases the GIL, so one chain's host work (priors,
+    transforms, tree bookkeeping) overlaps the others' GPU evaluations; evaluations of different contexts on one
+    device are serialised by the library."""
+    t0 = time.perf_counter()
+    if isinstance(model, (list, tuple)):
+        import threading
+        models = list(model)
+        if len(models) != num_chains:
+            raise ValueError("need one model per chain")
+        chains = [None] * num_chains
+        errors = []
+
+        def work(c):
+            try:
+                chains[c] = run_chain(models[c], num_warmup, num_samples, seed=seed + c, **kw)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(c,)) for c in range(num_chains)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        warm = max(c["warmup_s"] for c in chains)
+        samp = max(c["sampling_s"] for c in chains)
+    else:
+        chains = [run_chain(model, num_warmup, num_samples, seed=seed + c, **kw) for c in range(num_chains)]
+        warm = sum(c["warmup_s"] for c in chains)
+        samp = sum(c["sampling_s"] for c in chains)
     x = np.stack([c["x"] for c in chains])                      # [chain, draw, site]
     return {"x": x, "chains": chains, "ess_bulk": np.array([ess_bulk(x[:, :, i]) for i in range(x.shape[2])]),
             "rhat": np.array([split_rhat(x[:, :, i]) for i in range(x.shape[2])]),
-            "warmup_s": sum(c["warmup_s"] for c in chains), "sampling_s": sum(c["sampling_s"] for c in chains),
+            "warmup_s": warm, "sampling_s": samp, "wall_s": time.perf_counter() - t0,
             "n_leapfrog_total": sum(c["n_leapfrog_total"] for c in chains)}
 
 

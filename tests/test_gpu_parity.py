@@ -283,3 +283,31 @@ def test_unsorted_upload_gives_the_same_answer(hl):
     b = hl(*cat.as_args(), sort=False)(THETA_DEFAULT)
     assert _close(a.loglike, b.loglike, rtol=1e-13) and _close(a.neff, b.neff, rtol=1e-12)
     assert _close(a.dloglike, b.dloglike, rtol=1e-12, floor=max(1.0, float(np.max(np.abs(b.dloglike)))))
+
+
+def test_sampler_potential_fast_path_matches_evaluate(golden_dir):
+    """PopCosmoModel.potential (raw library call + plain-float chain rule) against the documented composition
+    priors.constrain / log_prior / evaluate, and against finite differences in unconstrained space."""
+    from bumpcosmology_b200 import intensity_models as im, priors
+    g = _load(golden_dir, "small")
+    model = im.pop_cosmo_model(*_data(g))
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        u = rng.uniform(-1, 1, priors.NSITES)
+        U, grad, rec = model.potential(u)
+        x, dx, lj, dlj = priors.constrain(u)
+        lp, glp = priors.log_prior(x)
+        ev = model.evaluate(x)
+        gg = glp.copy()
+        gg[:14] += ev["dloglike_dsite"] + ev["dselfactor_dsite"]
+        assert _close(U, -(lp + lj + ev["loglike"] + ev["selfactor"]), rtol=1e-12)
+        assert _close(grad, -(gg * dx + dlj), rtol=1e-11, floor=max(1.0, float(np.max(np.abs(grad)))))
+        d = model.deterministics(rec)
+        assert _close(d["R"], ev["R"], rtol=1e-12) and _close(d["neff"], ev["neff"], rtol=1e-12)
+        for i in (3, 9, 11):   # a, beta, lam: smooth directions
+            up, um = u.copy(), u.copy()
+            up[i] += 1e-6
+            um[i] -= 1e-6
+            fd = (model.potential(up)[0] - model.potential(um)[0]) / 2e-6
+            assert abs(fd - grad[i]) <= 1e-5 * max(1.0, abs(fd))
+    model.close()

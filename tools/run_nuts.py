@@ -16,9 +16,15 @@ ap.add_argument("--chains", type=int, default=4)
 ap.add_argument("--seed", type=int, default=1652819403)   # run_cosmo_fit.py:19
 ap.add_argument("--progress", type=int, default=0)
 ap.add_argument("--out", default="")
+ap.add_argument("--sequential", action="store_true", help="one context, chains one after another")
 a = ap.parse_args()
 cat = make_catalog(a.workload)
-model = im.pop_cosmo_model(*cat.as_args())
+if a.sequential:
+    model = im.pop_cosmo_model(*cat.as_args())
+    models = [model]
+else:   # one context per chain, chains in threads (the reference's chains run in parallel as well)
+    models = [im.pop_cosmo_model(*cat.as_args()) for _ in range(a.chains)]
+    model = models
 t0 = time.perf_counter()
 r = nuts.run_mcmc(model, a.warmup, a.samples, a.chains, seed=a.seed, progress=a.progress or None)
 wall = time.perf_counter() - t0
@@ -30,7 +36,8 @@ line = {
     "warmup_s": r["warmup_s"], "ess_min": float(ess.min()), "ess_min_site": priors.SITE_NAMES[int(ess.argmin())],
     "ess_per_s_total": float(ess.min() / wall), "ess_per_s_sampling": float(ess.min() / r["sampling_s"]),
     "rhat_max": float(r["rhat"][:14].max()), "n_leapfrog": int(r["n_leapfrog_total"]),
-    "evals_per_s": r["n_leapfrog_total"] / wall, "model_evals": model.n_evals,
+    "evals_per_s": r["n_leapfrog_total"] / wall, "model_evals": sum(m.n_evals for m in models),
+    "chains_in_parallel": not a.sequential,
     "divergences": int(sum(c["stats"]["diverging"].sum() for c in r["chains"])),
     "mean_accept": float(np.mean([c["stats"]["accept"].mean() for c in r["chains"]])),
     "mean_depth": float(np.mean([c["stats"]["depth"].mean() for c in r["chains"]])),
