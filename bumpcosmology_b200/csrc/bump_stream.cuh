@@ -1,4 +1,4 @@
-// The streaming kernel: one pass over the SoA sample / injection columns producing, per tile, the shifted sums
+// The streaming kernel: one pass over the SoA sample / injection columns producing, per (warp, event) record, the shifted sums
 //   S = sum e^{w-m},  S2 = sum e^{2(w-m)}  and the 17 gradient features  sum e^{w-m} f_k.
 //
 // Replaces intensity_models.py:378-381 (events) and :385-388 (injections) — z_of_dL, detector->source masses,
@@ -11,7 +11,7 @@
 // where lin collects every term that is linear in precomputed logs, so a sample costs 8 exp, 4 reciprocals
 // and NO logarithm; softmax-weighted gradient terms are products of the same factors (no divisions).
 // The shift m is per thread: the `lin` of its first finite-weight sample, raised only when a later sample
-// exceeds it by e^RESCALE_GAP (fp64 has the range to carry everything else); threads and tiles are merged
+// exceeds it by e^RESCALE_GAP (fp64 has the range to carry everything else); lanes, records and ranks are merged
 // with the usual (max, rescale) rule, so the result equals the reference's max-shifted logsumexp.
 #pragma once
 #include <cuda_runtime.h>
