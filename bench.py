@@ -105,19 +105,49 @@ def workload_catalog(name):
     return cat, time.time() - t0
 
 
-def cpu_baseline(cat, frac_events, frac_sel, evals, warm, threads=None):
-    """The oracle port (torch fp64, autograd) on the host cores, on a bounded sample of the workload.
-    Returns evals/s extrapolated linearly to the full workload, and the sample description."""
+def _sample_of(cat, frac):
+    ne = max(1, int(round(cat.nobs * frac)))
+    ns = max(1, int(round(cat.nsel * frac)))
+    data = (cat.m1s_det[:ne], cat.qs[:ne], cat.dls[:ne], cat.pdraw[:ne], cat.m1s_det_sel[:ns], cat.qs_sel[:ns],
+            cat.dls_sel[:ns], cat.pdraw_sel[:ns], cat.Ndraw)
+    n_sample = ne * cat.nsamp + ns
+    desc = (f"{ne} of {cat.nobs} events x {cat.nsamp} samples + {ns} of {cat.nsel} injections "
+            f"({100 * n_sample / cat.n_elements:.2f}% of the workload's elements)")
+    return data, n_sample / cat.n_elements, desc
+
+
+def cpu_port_cpp(cat, frac, evals, warm):
+    """oracle/bump_cpu.cpp: fused single-pass C++/OpenMP port, all host threads.  Returns (evals/s extrapolated
+    linearly to the full workload, per-eval seconds on the sample, sample description, threads) or None."""
+    try:
+        from oracle import bump_cpu
+        data, scale, desc = _sample_of(cat, frac)
+        port = bump_cpu.CpuPort(*data)
+    except Exception as e:  # noqa: BLE001  (no compiler on the box, ...)
+        print(f"[bench] C++ CPU port unavailable: {e}", file=sys.stderr)
+        return None
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas
+    thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(7, seed=5)])
+    for i in range(warm):
+        port.evaluate(thetas[i % len(thetas)])
+    ts = []
+    for i in range(evals):
+        t0 = time.perf_counter()
+        port.evaluate(thetas[i % len(thetas)])
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    threads = port.threads
+    port.close()
+    return scale / t, t, desc, threads
+
+
+def cpu_port_torch(cat, frac, evals, warm):
+    """oracle/bump_oracle.py: the parity oracle (eager torch fp64 + autograd), all host threads."""
     import torch
 
     from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas
     from oracle import bump_oracle as bo
-    if threads:
-        torch.set_num_threads(threads)
-    ne = max(1, int(round(cat.nobs * frac_events)))
-    ns = max(1, int(round(cat.nsel * frac_sel)))
-    data = (cat.m1s_det[:ne], cat.qs[:ne], cat.dls[:ne], cat.pdraw[:ne], cat.m1s_det_sel[:ns], cat.qs_sel[:ns],
-            cat.dls_sel[:ns], cat.pdraw_sel[:ns], cat.Ndraw)
+    data, scale, desc = _sample_of(cat, frac)
     thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(7, seed=5)])
     chunk = max(1, 2_000_000 // max(cat.nsamp, 1))
     for i in range(warm):
@@ -127,31 +157,50 @@ def cpu_baseline(cat, frac_events, frac_sel, evals, warm, threads=None):
         t0 = time.perf_counter()
         bo.evaluate(thetas[i % len(thetas)], data, grad=True, event_chunk=chunk)
         ts.append(time.perf_counter() - t0)
-    n_sample = ne * cat.nsamp + ns
-    scale = n_sample / cat.n_elements
-    t_full = float(np.median(ts)) / scale
-    sample = (f"{ne} of {cat.nobs} events x {cat.nsamp} samples + {ns} of {cat.nsel} injections "
-              f"({100 * scale:.2f}% of the workload's elements), {evals} evals after {warm} warm-ups, median, "
-              "extrapolated linearly in element count")
-    return 1.0 / t_full, sample, float(np.median(ts)), torch.get_num_threads()
+    t = float(np.median(ts))
+    return scale / t, t, desc, torch.get_num_threads()
+
+
+def cpu_baseline(cat, evals=8, warm=2):
+    """Both CPU stand-ins for "the reference's JAX on the host cores"  on bounded samples of
+    the workload; the FASTER one is the reported baseline."""
+    out = {}
+    cpp = cpu_port_cpp(cat, min(1.0, 6_000_000 / cat.n_elements), evals, warm)
+    if cpp:
+        out["cpp_openmp"] = {"value": cpp[0], "sample_s_per_eval": cpp[1], "sample": cpp[2], "cores": cpp[3]}
+    tv = cpu_port_torch(cat, min(1.0, 900_000 / cat.n_elements), max(3, evals // 2), 1)
+    out["torch_eager"] = {"value": tv[0], "sample_s_per_eval": tv[1], "sample": tv[2], "cores": tv[3]}
+    best = max(out, key=lambda k: out[k]["value"])
+    b = out[best]
+    return {"value": b["value"], "unit": UNIT, "cores": b["cores"], "kind": "port", "engine": best,
+            "sample": b["sample"] + f", {evals} evals after {warm} warm-ups, median, extrapolated linearly in "
+                                    "element count",
+            "sample_s_per_eval": b["sample_s_per_eval"], "host_cpus": os.cpu_count(), "engines": out}
 
 
 def run_reference(args, rank):
+    """The reference arm: the reference's algorithm on the host cores.  The reference itself (JAX/numpyro) is not
+    installable in this image, so this times the faster CPU port of oracle/ (normally the fused C++/OpenMP one)."""
     if rank != 0:
         return
     cat, _ = workload_catalog(args.workload)
-    # ~1.5 % of O5 per step keeps the whole arm within a few minutes on any host
-    frac = min(1.0, 900_000 / cat.n_elements)
-    v, sample, t_step, threads = cpu_baseline(cat, frac, frac, args.steps, args.warmup)
+    frac = min(1.0, 6_000_000 / cat.n_elements)      # 10 % of O5 per step: the whole arm stays within a few minutes
+    cpp = cpu_port_cpp(cat, frac, args.steps, args.warmup)
+    if cpp:
+        v, t_step, sample, threads = cpp
+        engine = "cpp_openmp (oracle/bump_cpu.cpp: fused single pass, log space, libm)"
+    else:
+        v, t_step, sample, threads = cpu_port_torch(cat, min(1.0, 900_000 / cat.n_elements), args.steps, args.warmup)
+        engine = "torch_eager (oracle/bump_oracle.py)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections",
-                   "note": "reference JAX stack is not installable here; CPU arm = oracle port (torch fp64 + "
-                           "autograd restatement of intensity_models.py:357-401), all host threads"},
+                   "note": "reference JAX stack is not installable here; CPU arm = " + engine + ", all host threads; "
+                           "each step is one logL+grad evaluation of a bounded sample, extrapolated linearly"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "sample_s_per_eval": t_step, "host_cpus": os.cpu_count()},
+                         "sample_s_per_eval": t_step, "host_cpus": os.cpu_count(), "engine": engine},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -325,10 +374,7 @@ def main():
         "result_check": {"logl": res.logl, "neff_sel": res.neff_sel},
     }
     if world == 1 and not args.no_cpu_baseline and not args.wa:
-        frac = min(1.0, 900_000 / cat.n_elements)
-        v, sample, t_step, threads = cpu_baseline(cat, frac, frac, evals=8, warm=2)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                                "sample_s_per_eval": t_step, "host_cpus": os.cpu_count()}
+        line["cpu_baseline"] = cpu_baseline(cat)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
