@@ -43,7 +43,7 @@ constexpr int SRCH_OCTAVES = 21;          // 2^-8 .. 2^13 Gpc
 constexpr int SRCH_N = SRCH_OCTAVES << SRCH_MBITS;   // 5376 uint16 entries
 constexpr int SRCH_DOUBLES = SRCH_N / 4;
 
-constexpr int NEXPT = 64;    // 2^(j/64) (bump_math.cuh fexp)
+constexpr int NEXPT = 2048;  // 2^(j/2048) (bump_math.cuh fexp); theta-independent, written once per context
 constexpr int OFF_SCAL = 0;
 constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT]
 constexpr int OFF_COS = OFF_EXPT + NEXPT;               // double2 cos[NCPAIR][NZ]
@@ -55,6 +55,7 @@ constexpr int BLOB_BYTES = BLOB_DOUBLES * 8;
 static_assert(BLOB_BYTES % 16 == 0, "bulk copies need 16-byte multiples");
 static_assert(SRCH_N % 4 == 0, "search table must fill whole doubles");
 static_assert(OFF_EXPT % 16 == 0, "the exp table must sit on a 128-byte boundary");
+static_assert((NEXPT & (NEXPT - 1)) == 0, "the exp table size is a power of two");
 
 // cosmology pair records, bin b = [knot b, knot b+1]
 enum CosRec { CR_DL = 0,   // {dl_b, 1/(dl_{b+1}-dl_b)}
@@ -100,8 +101,8 @@ struct Work {
     int64_t n_evt_groups;  // nobs * g_evt
     int64_t n_groups;      // + groups of the injection set
     int64_t gpw;           // groups per warp (last warps may own fewer / none)
-    int64_t evt_stride;    // padded samples per event (even)
-    int64_t sel_stride;    // padded injections (even)
+    int64_t evt_stride;    // padded samples per event (multiple of GROUP: the kernel loads whole groups unpredicated)
+    int64_t sel_stride;    // padded injections (multiple of GROUP)
     int32_t nobs;
     int32_t nwarps;
 };

@@ -236,7 +236,7 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     ds = DataSet();
     ds.nrows = nrows;
     ds.ncols = ncols;
-    ds.stride = (ncols + 1) & ~int64_t(1);
+    ds.stride = (ncols + GROUP - 1) / GROUP * GROUP;   // whole 64-sample groups: the kernel's loads are unpredicated
     c->plan_dirty = true;
     const int64_t n = nrows * ncols, npad = nrows * ds.stride;
     if (npad == 0) return BUMP_OK;
@@ -480,6 +480,11 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaMalloc(&c->d_aux, sizeof(double) * (AUX_DOUBLES + AUX_CHAIN_DOUBLES)));
     CK(cudaMalloc(&c->d_blob, BLOB_BYTES));
     CK(cudaMemset(c->d_blob, 0, BLOB_BYTES));
+    {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
+        std::vector<double> expt(NEXPT);
+        for (int j = 0; j < NEXPT; ++j) expt[j] = (double)exp2l((long double)j / NEXPT);
+        CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * NEXPT, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
     // [0] unused, [1] epilogue ticket, [2] bad-theta flag, [3] bad-input flag, [4..7] cosmology scan-chain flags
     CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8));

@@ -68,6 +68,11 @@ __device__ __forceinline__ void stage_tables(double* s_blob, uint64_t* mbar, con
     }
 }
 
+template <int V>
+struct IC {   // integral constant (table ids as template arguments of generic lambdas)
+    static constexpr int value = V;
+};
+
 struct ThreadAcc {
     double m;           // shift
     double a[NACC];     // S, S2, features
@@ -89,32 +94,45 @@ struct MassEval {
     double sgm;      // m * e/(1+e) : m times the turn-on's logistic weight
     double slope;    // dP/dm inside the bin
     double m, u;
-    int b;
+    uint32_t b;      // shared-window address of the bin's records (blob base + 16 b)
 };
 
-__device__ __forceinline__ void mass_eval(const double m, const double lm, const double2* __restrict__ mass,
-                                          const double* __restrict__ expt, MassEval& o) {
+constexpr int MASS_BYTES = OFF_MASS * 8;   // byte offsets of the tables inside the blob
+constexpr int COS_BYTES = OFF_COS * 8;
+constexpr int CTAN_BYTES = OFF_CTAN * 8;
+constexpr int SRCH_BYTES = OFF_SRCH * 8;
+
+// `sb` = shared-window address of the table blob
+__device__ __forceinline__ void mass_eval(const double m, const double lm, const uint32_t sb, MassEval& o) {
     const double y = (m - K_SC[S_M]) * K_SC[S_INV_DM];
-    const double e = fexp(-y, expt);
+    const double e = fexp<false>(-y, sb);
     const double s1 = frcp(1.0 + e);
     o.sgm = (e * s1) * m;
     o.lrel = lm - K_SC[S_LOG_M];
-    o.EQ = fexp(-K_SC[S_C] * o.lrel, expt) * (K_SC[S_C2] * s1);
+    o.EQ = fexp<false>(-K_SC[S_C] * o.lrel, sb) * (K_SC[S_C2] * s1);
     const double pos = (m - MIN_BH_MASS) * K_SC[S_INV_DMBH];
     int b = __double2int_rd(pos);
     b = min(max(b, 0), NM - 2);
     o.u = pos - (double)b;
-    const double2 g = mass[MR_G * NM + b];
-    const double eP = fexp(fma(o.u, g.y, g.x), expt);
+    o.b = sb + 16u * (uint32_t)b;
+    const double2 g = lds128<MASS_BYTES + MR_G * NM * 16>(o.b);
+    const double eP = fexp<false>(fma(o.u, g.y, g.x), sb);
     o.EP = (m < K_SC[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
     o.slope = g.y * K_SC[S_INV_DMBH];
     o.m = m;
-    o.b = b;
 }
 
 // Feature contributions of one mass evaluation, weighted by wp = (weight of the sample) / (EP + EQ).
-__device__ __forceinline__ double mass_features(const MassEval& o, const double wp,
-                                                const double2* __restrict__ mass, double* __restrict__ a) {
+template <int K>
+__device__ __forceinline__ void mass_tangents(const MassEval& o, const double wP, double* __restrict__ a) {
+    if constexpr (K < 5) {
+        const double2 t = lds128<MASS_BYTES + (MR_GA + K) * NM * 16>(o.b);
+        a[2 + F_PA + K] = fma(wP, fma(o.u, t.y, t.x), a[2 + F_PA + K]);
+        mass_tangents<K + 1>(o, wP, a);
+    }
+}
+
+__device__ __forceinline__ double mass_features(const MassEval& o, const double wp, double* __restrict__ a) {
     const double wQ = wp * o.EQ, wP = wp * o.EP;
     a[2 + F_SQ] += wQ;
     a[2 + F_C] = fma(wQ, o.lrel, a[2 + F_C]);
@@ -122,11 +140,7 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
     a[2 + F_T] += wQs;
     const double wPs = wP * o.slope;
     a[2 + F_GEO] = fma(wPs, o.m - MIN_BH_MASS, a[2 + F_GEO]);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const double2 t = mass[(MR_GA + k) * NM + o.b];
-        a[2 + F_PA + k] = fma(wP, fma(o.u, t.y, t.x), a[2 + F_PA + k]);
-    }
+    mass_tangents<0>(o, wP, a);
     // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c)
     return fma(wPs, o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
 }
@@ -137,9 +151,7 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
 template <bool WA, class Mid>
 __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
                                                   const double lq, const double l1q, const double lpd,
-                                                  const double* __restrict__ s_blob, ThreadAcc& A, Mid&& mid) {
-    const double* __restrict__ expt = s_blob + OFF_EXPT;
-    const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
+                                                  const uint32_t sb, ThreadAcc& A, Mid&& mid) {
     double m2 = q * m1;
     double lm2 = lm1 + lq;
     const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);   // :149
@@ -150,27 +162,27 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM], L, -lpd);   // :332 (no (1+z)^-2 Jacobian here)
     mid();
     if (valid && lin - A.m > RESCALE_GAP) {
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb);
         A.a[0] *= s;
         A.a[1] *= s * s;
 #pragma unroll
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
     }
-    const double E = valid ? fexp(lin - A.m, expt) : 0.0;
+    const double E = valid ? fexp<true>(lin - A.m, sb) : 0.0;
     A.nvalid += valid ? 1 : 0;
-    const double r = fexp(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), expt);
+    const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb);
     const double sr = frcp(1.0 + r);
     MassEval M1, M2;
-    mass_eval(m1, lm1, mass, expt, M1);
-    mass_eval(m2, lm2, mass, expt, M2);
+    mass_eval(m1, lm1, sb, M1);
+    mass_eval(m2, lm2, sb, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     const double base = sr * E;
     const double p = (sum1 * sum2) * base;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    mass_features(M1, sum2 * base, mass, A.a);
-    mass_features(M2, sum1 * base, mass, A.a);
+    mass_features(M1, sum2 * base, A.a);
+    mass_features(M2, sum1 * base, A.a);
     const double psig = p * (r * sr);
     A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
@@ -184,27 +196,26 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
 template <bool WA, class Mid>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
-                                            const double* __restrict__ s_blob, ThreadAcc& A, Mid&& mid) {
-    const double* __restrict__ expt = s_blob + OFF_EXPT;
-    const double2* __restrict__ cos = reinterpret_cast<const double2*>(s_blob + OFF_COS);
-    const double* __restrict__ ctan = s_blob + OFF_CTAN;
-    const unsigned short* __restrict__ srch = reinterpret_cast<const unsigned short*>(s_blob + OFF_SRCH);
-    const double2* __restrict__ mass = reinterpret_cast<const double2*>(s_blob + OFF_MASS);
-
+                                            const uint32_t sb, ThreadAcc& A, Mid&& mid) {
     // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
-    // bucket table keyed by the top bits of x gives a lower bound of the bin; walk up to the exact one (a bucket
-    // is narrower than any bin, so this is at most one step; measured faster than a branch-free two-record select).
+    // The bucket table, keyed by the top bits of x, gives a lower bound b0 of the bin.  A bucket (1/256 octave) is
+    // narrower than any bin of the d_L grid (log dl_{k+1} - log dl_k >= ZSTEP = 0.0045 > log(1 + 1/256)), so the
+    // bin is b0 or b0 + 1: one comparison with knot b0 + 1, no loop.  (records_kernel flags the evaluation as bad
+    // if theta is so extreme that the ends of the bucket range break this: h > 3.4 or h < 0.05.)
     int j = (__double2hiint(x) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
     j = min(max(j, 0), SRCH_N - 1);
-    int b = srch[j];
-    while (b < NZ - 2 && x >= cos[CR_DL * NZ + b + 1].x) ++b;
-    const double2 rdl = cos[CR_DL * NZ + b];
+    const uint32_t b0 = lds16<SRCH_BYTES>(sb + 2u * (uint32_t)j);
+    const double knot = lds64<COS_BYTES + CR_DL * NZ * 16 + 16>(sb + 16u * b0);   // dl[b0 + 1]
+    const uint32_t b = min(b0 + (x >= knot ? 1u : 0u), (uint32_t)(NZ - 2));
+    const uint32_t ab = sb + 16u * b;   // the bin's pair records
+    const uint32_t at = sb + 8u * b;    // the bin's tangent-table knots
+    const double2 rdl = lds128<COS_BYTES + CR_DL * NZ * 16>(ab);
     const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     double t = (x - rdl.x) * rdl.y;
     const double idl = beyond ? 0.0 : rdl.y;
     t = beyond ? 1.0 : t;
     // ---- position inside the z bin: 1+z = (1+z_b)(1 + t eps)
-    const double2 rz = cos[CR_Z * NZ + b];
+    const double2 rz = lds128<COS_BYTES + CR_Z * NZ * 16>(ab);
     const double zeps = K_SC[S_ZEPS];
     const double te = t * zeps;
     const double u1 = frcp1p_small(te);
@@ -216,8 +227,8 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     double lm1 = lm - L;
     double lm2 = lm1 + lq;
     // ---- dVC/dz and d(dL)/dz lerps at z (:264-268), same bin, same t
-    const double2 rvc = cos[CR_DVC * NZ + b];
-    const double2 rdd = cos[CR_DDL * NZ + b];
+    const double2 rvc = lds128<COS_BYTES + CR_DVC * NZ * 16>(ab);
+    const double2 rdd = lds128<COS_BYTES + CR_DDL * NZ * 16>(ab);
     const double dvc = fma(t, rvc.y, rvc.x);
     const double ddl = fma(t, rdd.y, rdd.x);
     const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN) && (dvc > 0.0);   // :149; log(dVc/dz = 0) = -inf
@@ -230,24 +241,24 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM2], L, -lpd);
     mid();
     if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp(A.m - lin, expt);
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb);
         A.a[0] *= s;
         A.a[1] *= s * s;
 #pragma unroll
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
     }
-    const double E = valid ? fexp(lin - A.m, expt) : 0.0;
+    const double E = valid ? fexp<true>(lin - A.m, sb) : 0.0;
     A.nvalid += valid ? 1 : 0;
     // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
     const double kappa = K_SC[S_KAPPA];
-    const double r = fexp(kappa * (L - K_SC[S_LOPZP]), expt);
+    const double r = fexp<false>(kappa * (L - K_SC[S_LOPZP]), sb);
     const double sr = frcp(1.0 + r);
     const double sig = r * sr;
     // ---- mass function at both masses
     MassEval M1, M2;
-    mass_eval(m1, lm1, mass, expt, M1);
-    mass_eval(m2, lm2, mass, expt, M2);
+    mass_eval(m1, lm1, sb, M1);
+    mass_eval(m2, lm2, sb, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     // ---- the weight and its partial products
     const double base = (sr * iddl) * E;            // everything but the masses and dVc/dz
@@ -256,7 +267,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double bv = base * dvc;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    const double md = mass_features(M1, sum2 * bv, mass, A.a) + mass_features(M2, sum1 * bv, mass, A.a);
+    const double md = mass_features(M1, sum2 * bv, A.a) + mass_features(M2, sum1 * bv, A.a);
     // ---- d w / d t at fixed tables (times p), then the cosmological tangents
     const double lt = zeps * u1;                    // d log1p(z) / dt
     const double psig = p * sig;
@@ -264,15 +275,17 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double pWx = pWt * idl;                   // -pWx * (d dl-table/d theta)(t) = p (dw/dt)(dt/dtheta)
     A.a[2 + F_CZ] = fma(pWx, x, A.a[2 + F_CZ]);
     const double pid = p * iddl;
-    auto tangent = [&](const int tdl, const int tdvc, const int tddl, double& acc) {
-        const double a0 = ctan[tdl * NZ + b], a1 = ctan[tdl * NZ + b + 1];
-        const double v0 = ctan[tdvc * NZ + b], v1 = ctan[tdvc * NZ + b + 1];
-        const double d0 = ctan[tddl * NZ + b], d1 = ctan[tddl * NZ + b + 1];
+    auto tangent = [&](auto tdl, auto tdvc, auto tddl, double& acc) {
+        constexpr int ODL = CTAN_BYTES + decltype(tdl)::value * NZ * 8, ODVC = CTAN_BYTES + decltype(tdvc)::value * NZ * 8,
+                      ODDL = CTAN_BYTES + decltype(tddl)::value * NZ * 8;
+        const double a0 = lds64<ODL>(at), a1 = lds64<ODL + 8>(at);
+        const double v0 = lds64<ODVC>(at), v1 = lds64<ODVC + 8>(at);
+        const double d0 = lds64<ODDL>(at), d1 = lds64<ODDL + 8>(at);
         acc = fma(-pWx, fma(t, a1 - a0, a0), fma(p0, fma(t, v1 - v0, v0), fma(-pid, fma(t, d1 - d0, d0), acc)));
     };
-    tangent(CT_DL_OM, CT_DVC_OM, CT_DDL_OM, A.a[2 + F_OM]);
-    tangent(CT_DL_W, CT_DVC_W, CT_DDL_W, A.a[2 + F_W]);
-    if constexpr (WA) tangent(CT_DL_WA, CT_DVC_WA, CT_DDL_WA, A.a[2 + F_WA]);
+    tangent(IC<CT_DL_OM>{}, IC<CT_DVC_OM>{}, IC<CT_DDL_OM>{}, A.a[2 + F_OM]);
+    tangent(IC<CT_DL_W>{}, IC<CT_DVC_W>{}, IC<CT_DDL_W>{}, A.a[2 + F_W]);
+    if constexpr (WA) tangent(IC<CT_DL_WA>{}, IC<CT_DVC_WA>{}, IC<CT_DDL_WA>{}, A.a[2 + F_WA]);
     A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
     A.a[2 + F_SIG] += psig;
@@ -308,8 +321,9 @@ __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ ou
 
 // Persistent, warp-autonomous streaming kernel.  After the table blob has been staged into shared memory (TMA
 // bulk copy, one mbarrier) no warp ever synchronises with another: warp w walks its range of 64-sample groups
-// [w*gpw, (w+1)*gpw), lane l evaluating samples 2l and 2l+1 of each group (one 128-bit load per column), and
-// flushes a record whenever the event changes.
+// [w*gpw, (w+1)*gpw), lane l evaluating samples l and 32+l of each group (two coalesced 64-bit loads per column),
+// and flushes a record whenever the event changes.  Every event (and the injection set) is padded to whole groups
+// with zero-weight sentinel samples at upload, so the loads carry no predicate.
 #ifdef BUMP_STREAM_MAXREG
 #define BUMP_STREAM_BOUNDS __maxnreg__(BUMP_STREAM_MAXREG)
 #else
@@ -324,6 +338,10 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + BLOB_BYTES);
 
     stage_tables(s_blob, mbar, g_blob);
+    // shared-window address of the blob, laundered so that it lives in one register for the whole kernel (the
+    // compiler otherwise rematerialises it - S2R, MOV, LEA - in front of every table access)
+    uint32_t sb = smem_u32(smem_raw);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb));
 
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
@@ -341,22 +359,19 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     int k = (e < wk.nobs) ? g0 - e * g_evt : g0 - n_evt_groups;
     ThreadAcc A;
     acc_init(A);
-    // Lane l evaluates samples l ("x half") and 32+l ("y half") of each 64-sample group: two fully coalesced
-    // 64-bit loads per column.  The loads are software-pipelined at half-group granularity — y(g) is issued
-    // before x(g) is evaluated, x(g+1) before y(g) is evaluated — so every load has one sample evaluation
-    // (~1000 cycles) to land, at no extra register cost; L2 prefetches run one further group ahead.
+    // The loads are software-pipelined at half-group granularity - y(g) is issued before x(g) is evaluated, x(g+1)
+    // from inside the evaluation of y(g) - so every load has one sample evaluation (~800 cycles) to land, at no
+    // extra register cost; L2 prefetches run one further group ahead.
     struct Half {
         double dl, m1, q, lm, lq, l1q, lpd;
     };
-    auto locate = [&](const int ee, const int kk, const double*& p0, int64_t& pitch, int& count) {
+    auto locate = [&](const int ee, const int kk, const double*& p0, int64_t& pitch) {
         const bool is_sel = ee >= wk.nobs;
         const int64_t stride = is_sel ? wk.sel_stride : wk.evt_stride;
         p0 = (is_sel ? cols.sel_base : cols.evt_base + (int64_t)ee * stride) + (int64_t)kk * GROUP + lane;
         pitch = is_sel ? cols.sel_pitch : cols.evt_pitch;
-        count = (int)min((int64_t)GROUP, stride - (int64_t)kk * GROUP);
     };
-    auto load_half = [&](const double* p, const int64_t pitch, const bool on) {
-        Half h{1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0};   // zero-weight sentinel (source mass below mbh_min)
+    auto load_half = [&](const double* p, const int64_t pitch) {
         // volatile: keeps the load where it is written (ptxas otherwise sinks it to its first use to save
         // registers, which exposes the full L2 latency once per group)
         auto ld = [](const double* a) {
@@ -364,27 +379,25 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
             asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
             return v;
         };
-        if (on) {
-            h.dl = ld(p + C_DL * pitch);
-            h.m1 = ld(p + C_M1D * pitch);
-            h.q = ld(p + C_Q * pitch);
-            h.lm = ld(p + C_LM * pitch);
-            h.lq = ld(p + C_LQ * pitch);
-            h.l1q = ld(p + C_L1Q * pitch);
-            h.lpd = ld(p + C_LPD * pitch);
-        }
+        Half h;
+        h.dl = ld(p + C_DL * pitch);
+        h.m1 = ld(p + C_M1D * pitch);
+        h.q = ld(p + C_Q * pitch);
+        h.lm = ld(p + C_LM * pitch);
+        h.lq = ld(p + C_LQ * pitch);
+        h.l1q = ld(p + C_L1Q * pitch);
+        h.lpd = ld(p + C_LPD * pitch);
         return h;
     };
     const double* p0;
     int64_t pitch;
-    int count;
-    locate(e, k, p0, pitch, count);
-    Half hx = load_half(p0, pitch, lane < count);
+    locate(e, k, p0, pitch);
+    Half hx = load_half(p0, pitch);
     for (int g = g0; g < g1; ++g) {
-        const Half hy = load_half(p0 + 32, pitch, 32 + lane < count);
+        const Half hy = load_half(p0 + 32, pitch);
         auto nothing = [] {};
-        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A, nothing);
-        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, s_blob, A, nothing);
+        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
+        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
         // consumed), and the group after it is pulled towards L2
         int e_next = e, k_next = k + 1;
@@ -395,15 +408,15 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         const bool more = g + 1 < g1;
         auto next_loads = [&] {
             if (more) {
-                locate(e_next, k_next, p0, pitch, count);
-                hx = load_half(p0, pitch, lane < count);
+                locate(e_next, k_next, p0, pitch);
+                hx = load_half(p0, pitch);
                 const double* pf = p0 - lane + GROUP + (lane & 3) * 16;   // 4 lines of 128 B per column
 #pragma unroll
                 for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
             }
         };
-        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A, next_loads);
-        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, s_blob, A, next_loads);
+        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
+        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);

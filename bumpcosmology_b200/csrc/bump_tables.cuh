@@ -351,9 +351,9 @@ tables_kernel(const double* __restrict__ theta, double* __restrict__ aux, unsign
 }
 
 // ---------------------------------------------------------------- kernel 2: packed records + scalars
-// One item per thread: NZ cosmology bins, NM mass bins, SRCH_N d_L buckets, NEXPT exp-table entries; the extra
-// last block derives the scalars (intensity_models.py:134-138,167-168) from a shared-memory copy of the PISN table.
-constexpr int REC_ITEMS = NZ + NM + SRCH_N + NEXPT;
+// One item per thread: NZ cosmology bins, NM mass bins, SRCH_N d_L buckets (the exp table of the blob is
+// theta-independent and written once at context creation); the extra last block derives the scalars (intensity_models.py:134-138,167-168) from a shared-memory copy of the PISN table.
+constexpr int REC_ITEMS = NZ + NM + SRCH_N;
 constexpr int REC_BLOCKS = (REC_ITEMS + PRO_THREADS - 1) / PRO_THREADS;   // + 1 block for the scalars
 
 __global__ void __launch_bounds__(PRO_THREADS)
@@ -369,6 +369,13 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
             build_scalars(th, aux, sm, ec, blob + OFF_SCAL, threadIdx.x);
         }
         if (threadIdx.x == 0) {
+            // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
+            // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
+            // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
+            // last two bins).  That takes h > 3.4 or h < 0.05, far outside the prior: flag it (-> NaN outputs).
+            const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
+            const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
+            if (!ec.fixed && (!(aux[AUX_DL + 2] >= first_hi) || !(aux[AUX_DL + NZ - 3] <= last_lo))) *flags = 1u;
             blob[OFF_SCAL + S_BAD] = (*flags != 0u) ? 1.0 : 0.0;
             *flags = 0u;
             for (int cc = 0; cc < COS_CHUNKS; ++cc) chain_flag[cc] = 0u;   // re-arm the scan chain of tables_kernel
@@ -424,8 +431,6 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
         srch[item] = (unsigned short)(item == 0 ? 0 : b);
         return;
     }
-    item -= SRCH_N;
-    if (item < NEXPT) blob[OFF_EXPT + item] = exp2((double)item / NEXPT);
 }
 
 }  // namespace bump
