@@ -114,11 +114,20 @@ __host__ __device__ inline int64_t group_event(const Work& w, const int64_t g) {
 constexpr int NCOL = 7;  // dl, m1det, q, log m1det, log q, log1p q, log pdraw
 enum Col { C_DL = 0, C_M1D, C_Q, C_LM, C_LQ, C_L1Q, C_LPD };
 
-struct Columns {   // column k of a set = base + k * pitch (one allocation per set)
-    const double* evt_base;
-    const double* sel_base;
-    int64_t evt_pitch, sel_pitch;
+// Resident data layout: group-blocked SoA.  A set (events, injections) is an array of BLOCKS, one per 64-sample
+// group, each holding the 7 columns of its group back to back (7 x 64 doubles = 3584 bytes = 28 lines of 128 B):
+//   sample s of group g, column k  ->  base[(g * NCOL + k) * GROUP + s]
+// Groups are stored in the order the streaming kernel numbers them, so a warp's range of groups is one contiguous
+// stretch of memory: its pointer advances by one block per group, every load is base + immediate offset, and a
+// half-warp of loads is still a fully used pair of 128-byte lines per column.
+constexpr int BLOCK_DOUBLES = NCOL * GROUP;
+struct Columns {
+    const double* evt_base;   // nobs * g_evt blocks
+    const double* sel_base;   // ceil(nsel / GROUP) blocks
 };
+__host__ __device__ inline int64_t block_index(const int64_t padded_sample, const int col) {
+    return ((padded_sample / GROUP) * NCOL + col) * GROUP + padded_sample % GROUP;
+}
 
 // ---- per-rank partial (multi-GPU exchange); doubles
 constexpr int PARTIAL_LEN = 128;  // sums [0,64) + copy of the scalar block [64,128)

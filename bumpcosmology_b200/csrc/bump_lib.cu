@@ -96,9 +96,6 @@ constexpr int NCCL_FLOAT64 = 8;   // ncclDouble in nccl.h
 
 // ---- upload-time kernel: raw (m1_det, q, d_L, pdraw) -> the 7 padded SoA columns (theta-independent logs hoisted;
 // the reference recomputes log(pdraw) on every trace, intensity_models.py:365)
-struct ColumnPtrs {
-    double* c[NCOL];
-};
 
 // Locality key of a sample: (row | coarse d_L bucket | fine m1_det).  Sorting the samples of an event (the
 // likelihood is a sum over them, so their order is free) makes the 32 lanes of a warp land in the same or in
@@ -119,7 +116,7 @@ __global__ void locality_keys_kernel(const double* __restrict__ m1d, const doubl
 __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const double* __restrict__ q,
                                        const double* __restrict__ dl, const double* __restrict__ pd,
                                        const unsigned int* __restrict__ perm, const int64_t nrows,
-                                       const int64_t ncols, const int64_t stride, ColumnPtrs out,
+                                       const int64_t ncols, const int64_t stride, double* __restrict__ out,
                                        unsigned int* __restrict__ bad, const double* __restrict__ fixed_tab) {
     const int64_t total = nrows * stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -132,14 +129,14 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
             if (!(vm > 0.0 && vq > 0.0 && dl[s] > 0.0 && pd[s] > 0.0 && isfinite(vm) && isfinite(vq) &&
                   isfinite(dl[s]) && isfinite(pd[s])))
                 atomicOr(bad, 1u);
-            out.c[C_M1D][i] = vm;
-            out.c[C_Q][i] = vq;
-            out.c[C_LM][i] = log(vm);
-            out.c[C_LQ][i] = log(vq);
-            out.c[C_L1Q][i] = log1p(vq);
+            out[block_index(i, C_M1D)] = vm;
+            out[block_index(i, C_Q)] = vq;
+            out[block_index(i, C_LM)] = log(vm);
+            out[block_index(i, C_LQ)] = log(vq);
+            out[block_index(i, C_L1Q)] = log1p(vq);
             if (!fixed_tab) {
-                out.c[C_DL][i] = dl[s];
-                out.c[C_LPD][i] = log(pd[s]);
+                out[block_index(i, C_DL)] = dl[s];
+                out[block_index(i, C_LPD)] = log(pd[s]);
             } else {
                 // fixed cosmology (pop_model, intensity_models.py:313-355): `dl` holds z; column 0 becomes log1p(z)
                 // and log dVdzdt(z) = log interp(z, zinterp, dVdzdt_interp) (:332) is folded into the pdraw column
@@ -150,26 +147,25 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
                 const double z0 = expm1(k * ZSTEP), z1 = (k + 1 == NZ - 1) ? expm1(LOG_ZMAX1) : expm1((k + 1) * ZSTEP);
                 double v = fixed_tab[k] + (z - z0) / (z1 - z0) * (fixed_tab[k + 1] - fixed_tab[k]);
                 if (z > z1 && k == NZ - 2) v = fixed_tab[NZ - 1];
-                out.c[C_DL][i] = lz;
-                out.c[C_LPD][i] = log(pd[s]) - log(v);
-                if (!(v > 0.0)) out.c[C_M1D][i] = 1.0;   // log dVdzdt = -inf: zero weight (sentinel mass)
+                out[block_index(i, C_DL)] = lz;
+                out[block_index(i, C_LPD)] = log(pd[s]) - log(v);
+                if (!(v > 0.0)) out[block_index(i, C_M1D)] = 1.0;   // log dVdzdt = -inf: zero weight (sentinel mass)
             }
         } else {   // sentinel padding: source mass 1/(1+z) < mbh_min -> weight exactly zero (-inf log weight)
-            out.c[C_DL][i] = 1.0;
-            out.c[C_M1D][i] = 1.0;
-            out.c[C_Q][i] = 1.0;
-            out.c[C_LM][i] = 0.0;
-            out.c[C_LQ][i] = 0.0;
-            out.c[C_L1Q][i] = LN2;
-            out.c[C_LPD][i] = 0.0;
+            out[block_index(i, C_DL)] = 1.0;
+            out[block_index(i, C_M1D)] = 1.0;
+            out[block_index(i, C_Q)] = 1.0;
+            out[block_index(i, C_LM)] = 0.0;
+            out[block_index(i, C_LQ)] = 0.0;
+            out[block_index(i, C_L1Q)] = LN2;
+            out[block_index(i, C_LPD)] = 0.0;
         }
     }
 }
 
 struct DataSet {
     int64_t nrows = 0, ncols = 0, stride = 0;   // events: [nobs, nsamp]; injections: [1, nsel]
-    double* base = nullptr;                     // NCOL * nrows * stride doubles
-    double* col(int c) const { return base + (size_t)c * nrows * stride; }
+    double* base = nullptr;                     // nrows * stride / GROUP blocks of NCOL * GROUP doubles
 };
 
 }  // namespace
@@ -240,14 +236,12 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     c->plan_dirty = true;
     const int64_t n = nrows * ncols, npad = nrows * ds.stride;
     if (npad == 0) return BUMP_OK;
-    CK(cudaMalloc(&ds.base, sizeof(double) * (NCOL * npad + 2 * GROUP)));   // slack: the kernel prefetches one group ahead
+    CK(cudaMalloc(&ds.base, sizeof(double) * NCOL * (npad + 2 * GROUP)));   // slack: the kernel prefetches two blocks ahead
     double* raw = nullptr;
     CK(cudaMalloc(&raw, sizeof(double) * 4 * n));
     const double* src[4] = {m1d, q, dl, pd};
     for (int k = 0; k < 4; ++k)
         CK(cudaMemcpyAsync(raw + (size_t)k * n, src[k], sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    ColumnPtrs cp;
-    for (int k = 0; k < NCOL; ++k) cp.c[k] = ds.col(k);
     const int blocks = (int)std::min<int64_t>((npad + 255) / 256, 148 * 16);
     unsigned int* perm = nullptr;
     unsigned long long *keys = nullptr, *keys_out = nullptr;
@@ -267,7 +261,7 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     }
     CK(cudaMemsetAsync(c->d_ticket + 3, 0, sizeof(unsigned int), c->stream));
     prepare_columns_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, raw + 3 * n, perm, nrows, ncols,
-                                                          ds.stride, cp, c->d_ticket + 3,
+                                                          ds.stride, ds.base, c->d_ticket + 3,
                                                           c->fixed ? c->d_fixed_tab : nullptr);
     CK(cudaGetLastError());
     unsigned int bad = 0;
@@ -328,8 +322,6 @@ Columns columns_of(const bump_ctx* c) {
     Columns cols;
     cols.evt_base = c->evt.base;
     cols.sel_base = c->sel.base;
-    cols.evt_pitch = c->evt.nrows * c->evt.stride;
-    cols.sel_pitch = c->sel.nrows * c->sel.stride;
     return cols;
 }
 

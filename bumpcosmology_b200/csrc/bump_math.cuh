@@ -75,7 +75,7 @@ __device__ __forceinline__ double fexp(const double x, const uint32_t sb) {
     p *= r;
     const double T = lds64<OFF_EXPT * 8>(sb + ((uint32_t)(n & (NEXPT - 1)) << 3));
     const double v = fma(T, p, T);
-    const int hi = __double2hiint(v) + ((max(n, -1010 * NEXPT) & ~(NEXPT - 1)) << 9);   // + ((n >> 11) << 20)
+    const int hi = (max(n, -1010 * NEXPT) & ~(NEXPT - 1)) * 512 + __double2hiint(v);   // + ((n >> 11) << 20): one IMAD
     return __hiloint2double(hi, __double2loint(v));
 }
 static_assert(NEXPT == 2048, "fexp's constants assume a 2048-entry table");

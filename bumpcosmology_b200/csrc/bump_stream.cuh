@@ -365,13 +365,13 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     struct Half {
         double dl, m1, q, lm, lq, l1q, lpd;
     };
-    auto locate = [&](const int ee, const int kk, const double*& p0, int64_t& pitch) {
-        const bool is_sel = ee >= wk.nobs;
-        const int64_t stride = is_sel ? wk.sel_stride : wk.evt_stride;
-        p0 = (is_sel ? cols.sel_base : cols.evt_base + (int64_t)ee * stride) + (int64_t)kk * GROUP + lane;
-        pitch = is_sel ? cols.sel_pitch : cols.evt_pitch;
+    // group g of the kernel's numbering lives in block g of the events buffer, or block g - n_evt_groups of the
+    // injection buffer: the pointer advances by one block per group and is re-based once, at the set boundary
+    auto block_of = [&](const int ee, const int kk) {
+        return (ee >= wk.nobs ? cols.sel_base + (int64_t)kk * BLOCK_DOUBLES
+                              : cols.evt_base + ((int64_t)ee * g_evt + kk) * BLOCK_DOUBLES) + lane;
     };
-    auto load_half = [&](const double* p, const int64_t pitch) {
+    auto load_half = [&](const double* p) {   // p = block + lane (x half) or block + 32 + lane (y half)
         // volatile: keeps the load where it is written (ptxas otherwise sinks it to its first use to save
         // registers, which exposes the full L2 latency once per group)
         auto ld = [](const double* a) {
@@ -380,26 +380,24 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
             return v;
         };
         Half h;
-        h.dl = ld(p + C_DL * pitch);
-        h.m1 = ld(p + C_M1D * pitch);
-        h.q = ld(p + C_Q * pitch);
-        h.lm = ld(p + C_LM * pitch);
-        h.lq = ld(p + C_LQ * pitch);
-        h.l1q = ld(p + C_L1Q * pitch);
-        h.lpd = ld(p + C_LPD * pitch);
+        h.dl = ld(p + C_DL * GROUP);
+        h.m1 = ld(p + C_M1D * GROUP);
+        h.q = ld(p + C_Q * GROUP);
+        h.lm = ld(p + C_LM * GROUP);
+        h.lq = ld(p + C_LQ * GROUP);
+        h.l1q = ld(p + C_L1Q * GROUP);
+        h.lpd = ld(p + C_LPD * GROUP);
         return h;
     };
-    const double* p0;
-    int64_t pitch;
-    locate(e, k, p0, pitch);
-    Half hx = load_half(p0, pitch);
+    const double* p0 = block_of(e, k);
+    Half hx = load_half(p0);
     for (int g = g0; g < g1; ++g) {
-        const Half hy = load_half(p0 + 32, pitch);
+        const Half hy = load_half(p0 + 32);
         auto nothing = [] {};
         if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
         else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
-        // consumed), and the group after it is pulled towards L2
+        // consumed), and the block after it is pulled towards L2 (28 lines: one per lane)
         int e_next = e, k_next = k + 1;
         if (k_next == ((e < wk.nobs) ? g_evt : n_groups - n_evt_groups)) {
             k_next = 0;
@@ -408,11 +406,10 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         const bool more = g + 1 < g1;
         auto next_loads = [&] {
             if (more) {
-                locate(e_next, k_next, p0, pitch);
-                hx = load_half(p0, pitch);
-                const double* pf = p0 - lane + GROUP + (lane & 3) * 16;   // 4 lines of 128 B per column
-#pragma unroll
-                for (int col = 0; col < NCOL; ++col) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + col * pitch));
+                p0 = (e_next == wk.nobs && k_next == 0) ? cols.sel_base + lane : p0 + BLOCK_DOUBLES;
+                hx = load_half(p0);
+                if (lane < BLOCK_DOUBLES / 16)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
             }
         };
         if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
