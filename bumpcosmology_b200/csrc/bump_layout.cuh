@@ -82,6 +82,8 @@ enum Scal {
     S_RATE0 = 42,    // lam - 3 - beta
     S_BAD = 43,      // 1 if theta or any table entry is not finite (outputs are then NaN)
     S_FIXED = 44,    // 1 in fixed-cosmology mode (pop_model): no gradient w.r.t. (h, Om, w)
+    S_LOG_C2 = 45,   // log 2 + log_pl_norm: the power-law tail's prefactor, folded into its exponent
+    S_POS0 = 46,     // -MIN_BH_MASS * S_INV_DMBH: position on the mbh grid = fma(m, S_INV_DMBH, S_POS0)
 };
 
 // ---- per-sample gradient features accumulated by the streaming kernel (DESIGN.md has the algebra)

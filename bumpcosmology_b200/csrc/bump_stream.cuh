@@ -92,7 +92,8 @@ struct MassEval {
     double EP, EQ;   // the two terms of the logaddexp, in linear space
     double lrel;     // log(m / mbhmax)
     double sgm;      // m * e/(1+e) : m times the turn-on's logistic weight
-    double slope;    // dP/dm inside the bin
+    double gy;       // G_{b+1} - G_b: dP/dm inside the bin, per grid step
+    double pos;      // (m - 3) / (grid step): position on the mbh grid
     double m, u;
     uint32_t b;      // shared-window address of the bin's records (blob base + 16 b)
 };
@@ -104,13 +105,14 @@ constexpr int SRCH_BYTES = OFF_SRCH * 8;
 
 // `sb` = shared-window address of the table blob
 __device__ __forceinline__ void mass_eval(const double m, const double lm, const uint32_t sb, MassEval& o) {
-    const double y = (m - K_SC[S_M]) * K_SC[S_INV_DM];
-    const double e = fexp<false>(-y, sb);
+    // -(m - M)/(0.05 M) = 20 - m/(0.05 M): one FMA
+    const double e = fexp<false>(fma(m, -K_SC[S_INV_DM], 1.0 / TURNON_WIDTH), sb);
     const double s1 = frcp(1.0 + e);
     o.sgm = (e * s1) * m;
     o.lrel = lm - K_SC[S_LOG_M];
-    o.EQ = fexp<false>(-K_SC[S_C] * o.lrel, sb) * (K_SC[S_C2] * s1);
-    const double pos = (m - MIN_BH_MASS) * K_SC[S_INV_DMBH];
+    o.EQ = fexp<false>(fma(o.lrel, -K_SC[S_C], K_SC[S_LOG_C2]), sb) * s1;   // 2 e^{lpn} (m/M)^-c / (1 + e)
+    const double pos = fma(m, K_SC[S_INV_DMBH], K_SC[S_POS0]);
+    o.pos = pos;
     int b = __double2int_rd(pos);
     b = min(max(b, 0), NM - 2);
     o.u = pos - (double)b;
@@ -118,7 +120,7 @@ __device__ __forceinline__ void mass_eval(const double m, const double lm, const
     const double2 g = lds128<MASS_BYTES + MR_G * NM * 16>(o.b);
     const double eP = fexp<false>(fma(o.u, g.y, g.x), sb);
     o.EP = (m < K_SC[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
-    o.slope = g.y * K_SC[S_INV_DMBH];
+    o.gy = g.y;
     o.m = m;
 }
 
@@ -138,11 +140,11 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
     a[2 + F_C] = fma(wQ, o.lrel, a[2 + F_C]);
     const double wQs = wQ * o.sgm;                         // wQ * m * logistic
     a[2 + F_T] += wQs;
-    const double wPs = wP * o.slope;
-    a[2 + F_GEO] = fma(wPs, o.m - MIN_BH_MASS, a[2 + F_GEO]);
+    const double wPg = wP * o.gy;
+    a[2 + F_GEO] = fma(wPg, o.pos, a[2 + F_GEO]);   // wP (dP/dm) (m - 3)
     mass_tangents<0>(o, wP, a);
     // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c)
-    return fma(wPs, o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
+    return fma(wPg * K_SC[S_INV_DMBH], o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
 }
 
 // Fixed-cosmology variant (the reference's `pop_model`, intensity_models.py:313-355): the sample carries source-frame

@@ -319,6 +319,8 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
     scal[S_EXP_LPN] = exp(lpn.v);
     scal[S_ZEPS] = expm1(ZSTEP);
     scal[S_C2] = 2.0 * exp(lpn.v);
+    scal[S_LOG_C2] = LN2 + lpn.v;
+    scal[S_POS0] = -MIN_BH_MASS * scal[S_INV_DMBH];
     scal[S_LAM2] = th[T_LAM] - 2.0;
     scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
