@@ -29,10 +29,15 @@ METRIC = "hyperlikelihood logL+grad evals/sec (O5 mock)"
 UNIT = "evals/s"
 ALGO_BYTES_PER_SAMPLE = 32           # m1_det, q, d_L, pdraw as fp64
 ALGO_FP64_INST_PER_SAMPLE = 700      # forward + 14-parameter gradient, FP64-pipe instructions
-# Measured with ncu on the same command (profiles/r01_o5_stream_kernel_opmix.txt / _ncu.txt): FP64-pipe warp
-# instructions the streaming kernel actually executes per 32 samples, and DRAM bytes it reads per sample.
-EXEC_FP64_INST_PER_SAMPLE = 256.5
-DRAM_BYTES_PER_SAMPLE = 56.1
+# Measured with ncu on the same command (profiles/r01b_o5_stream_kernel_opmix.txt / _ncu.txt): FP64-pipe warp
+# instructions the streaming kernel actually executes per 32 samples, DRAM bytes it reads per (real) sample, and the
+# issue cycles its instruction mix needs per warp-sample under the measured B200 issue rules
+# (profiles/r01_fp64_issue_microbench.txt: an FP64 instruction occupies its sub-partition for max(2, distinct
+# vector-register operands) cycles, every other instruction for ~1; nothing hides in the FP64 pipe's second cycle).
+EXEC_FP64_INST_PER_SAMPLE = 223.5
+EXEC_OTHER_INST_PER_SAMPLE = 189.2
+EXEC_FP64_3REG_PER_SAMPLE = 86.5
+DRAM_BYTES_PER_SAMPLE = 56.3
 
 
 def measured_peaks():
@@ -343,7 +348,19 @@ def main():
                 "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE, "algorithmic_frac": algo / pk["dfma_per_s"],
                 "note": "frac = FP64-pipe instructions the kernel executes (ncu, profiles/) x samples / kernel time, "
                         "over the DFMA issue rate measured by bump_peak in this run; algorithmic_frac uses SURVEY.md "
-                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 2.6x fewer"}
+                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 3.1x fewer"}
+        # issue ceiling of this instruction mix: 2 cycles per FP64 instruction, +1 for each with three distinct
+        # register operands, +1 per other instruction, per warp-sample and sub-partition (4 per SM)
+        cyc_model = 2 * EXEC_FP64_INST_PER_SAMPLE + EXEC_FP64_3REG_PER_SAMPLE + EXEC_OTHER_INST_PER_SAMPLE
+        sms = pk.get("sms", 148)
+        clk = pk.get("max_clock_mhz", 1965) * 1e6
+        cyc_meas = ker_ms * 1e-3 * clk * sms * 4 / (n_local / 32)
+        fp64["issue_model"] = {"cycles_per_warp_sample": cyc_model, "measured_cycles_per_warp_sample": cyc_meas,
+                               "frac": cyc_model / cyc_meas,
+                               "fp64_frac_at_model": 2 * EXEC_FP64_INST_PER_SAMPLE / cyc_model,
+                               "note": "what the kernel's own instruction mix allows under the issue rules measured by "
+                                       "tools/micro/fp64_operands.cu (profiles/r01_fp64_issue_microbench.txt); "
+                                       "shared-memory wavefronts run at 82 % of peak beside it"}
     value = K / (ms_total * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
