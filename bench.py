@@ -40,6 +40,20 @@ EXEC_FP64_3REG_PER_SAMPLE = 86.5
 DRAM_BYTES_PER_SAMPLE = 56.3
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too at the C level (NCCL prints its version
+    banner on communicator creation): park fd 1 on stderr for the run and emit the line on the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -183,7 +197,7 @@ def cpu_baseline(cat, evals=8, warm=2):
             "sample_s_per_eval": b["sample_s_per_eval"], "host_cpus": os.cpu_count(), "engines": out}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     """The reference arm: the reference's algorithm on the host cores.  The reference itself (JAX/numpyro) is not
     installable in this image, so this times the faster CPU port of oracle/ (normally the fused C++/OpenMP one)."""
     if rank != 0:
@@ -209,7 +223,7 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
 
 
 def main():
@@ -230,8 +244,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    out = OneLineStdout()
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, out)
 
     import torch
 
@@ -392,7 +407,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline and not args.wa:
         line["cpu_baseline"] = cpu_baseline(cat)
-    print(json.dumps(line), flush=True)
+    out.emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
