@@ -172,6 +172,7 @@ struct DataSet {
 
 struct bump_ctx {
     int device = 0;
+    int slot = 0;                     // constant-bank slot of the streaming kernel's scalars (0 .. NSLOT-1)
     uint32_t flags = 0;
     bool use_wa = false;
     bool fixed = false;               // fixed-cosmology mode (pop_model)
@@ -334,6 +335,23 @@ EvalConsts consts_of(const bump_ctx* c) {
     return ec;
 }
 
+// stream_kernel<WA, FIXED, SLOT> of a context (its mode and its constant-bank slot)
+using StreamKernel = void (*)(const Columns, const Work, const int*, const double*, double*);
+template <int SLOT>
+StreamKernel stream_kernel_of(const bool fixed, const bool wa) {
+    return fixed ? stream_kernel<false, true, SLOT> : wa ? stream_kernel<true, false, SLOT> : stream_kernel<false, false, SLOT>;
+}
+StreamKernel stream_kernel_at(const bool fixed, const bool wa, const int slot) {
+    switch (slot) {
+        case 0: return stream_kernel_of<0>(fixed, wa);
+        case 1: return stream_kernel_of<1>(fixed, wa);
+        case 2: return stream_kernel_of<2>(fixed, wa);
+        default: return stream_kernel_of<3>(fixed, wa);
+    }
+}
+static_assert(NSLOT == 4, "stream_kernel_at enumerates the slots");
+StreamKernel stream_kernel_for(const bump_ctx* c) { return stream_kernel_at(c->fixed, c->use_wa, c->slot); }
+
 // The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr) {
@@ -341,19 +359,12 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                                                           c->d_aux + AUX_DOUBLES, c->d_ticket + 4);
     records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c),
                                                           c->d_ticket + 4);
-    CK(cudaMemcpyToSymbolAsync(K_SC, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL, 0, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyToSymbolAsync(K_SC4, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL,
+                               sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
-    if (c->work.n_groups > 0) {
-        if (c->fixed)
-            stream_kernel<false, true><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
-                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
-        else if (c->use_wa)
-            stream_kernel<true, false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
-                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
-        else
-            stream_kernel<false, false><<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(
-                columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part);
-    }
+    if (c->work.n_groups > 0)
+        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work, c->d_rec_off,
+                                                                                  c->d_blob, c->d_part);
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
@@ -377,19 +388,24 @@ int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStrea
     return BUMP_OK;
 }
 
-// K_SC (constant bank) is shared by every context of a device: evaluations on one device are chained through an
-// event so that two contexts / streams never have an evaluation in flight at the same time.
-std::mutex g_dev_mutex;
-cudaEvent_t g_dev_event[64] = {};
+// A constant-bank slot (K_SC4[slot]) is shared by the contexts of a device that were assigned to it: their
+// evaluations are chained through an event so that two of them never have an evaluation in flight at the same time.
+// Contexts on different slots run concurrently.
+std::mutex g_dev_mutex;                  // slot assignment
+std::mutex g_slot_mutex[64 * NSLOT];     // launch order within a slot
+cudaEvent_t g_dev_event[64 * NSLOT] = {};
+int g_dev_next_slot[64] = {};
 
 struct DeviceChain {
     std::unique_lock<std::mutex> lock;
     cudaEvent_t ev = nullptr;
     cudaStream_t s;
-    DeviceChain(int device, cudaStream_t stream) : lock(g_dev_mutex), s(stream) {
-        if (device < 0 || device >= 64) return;
-        if (!g_dev_event[device]) cudaEventCreateWithFlags(&g_dev_event[device], cudaEventDisableTiming);
-        ev = g_dev_event[device];
+    DeviceChain(const bump_ctx* c, cudaStream_t stream) : s(stream) {
+        if (c->device < 0 || c->device >= 64) return;
+        const int k = c->device * NSLOT + c->slot;
+        lock = std::unique_lock<std::mutex>(g_slot_mutex[k]);
+        if (!g_dev_event[k]) cudaEventCreateWithFlags(&g_dev_event[k], cudaEventDisableTiming);
+        ev = g_dev_event[k];
         cudaStreamWaitEvent(s, ev, 0);
     }
     ~DeviceChain() {
@@ -424,7 +440,7 @@ int ensure_graph(bump_ctx* c) {
 int run_once(bump_ctx* c) {   // d_theta -> d_out on the context stream
     if (!(c->flags & BUMP_FLAG_NO_GRAPH))
         if (int r = ensure_graph(c)) return r;
-    DeviceChain chain(c->device, c->stream);
+    DeviceChain chain(c, c->stream);
     if (c->flags & BUMP_FLAG_NO_GRAPH) return launch_eval(c, c->d_theta, c->d_out, c->stream);
     CK(cudaGraphLaunch(c->graph, c->stream));
     return BUMP_OK;
@@ -485,9 +501,11 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_fixed_tab, sizeof(double) * NZ));
-    CK(cudaFuncSetAttribute(stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    if (device < 64) {   // round-robin over the constant-bank slots of this device
+        std::lock_guard<std::mutex> lk(g_dev_mutex);
+        c->slot = g_dev_next_slot[device]++ % NSLOT;
+    }
+    CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
     *out = c;
     return BUMP_OK;
 }
@@ -561,7 +579,7 @@ int bump_eval(bump_ctx* c, const double* theta, double* out) {
 int bump_eval_device(bump_ctx* c, const double* theta_dev, double* out_dev, void* stream) {
     if (!theta_dev || !out_dev) return fail(BUMP_E_INVALID, "null theta/out");
     if (int r = ensure_ready(c)) return r;
-    DeviceChain chain(c->device, static_cast<cudaStream_t>(stream));
+    DeviceChain chain(c, static_cast<cudaStream_t>(stream));
     return launch_eval(c, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -569,7 +587,7 @@ int bump_eval_partial_device(bump_ctx* c, const double* theta_dev, double* parti
                              void* stream) {
     if (!theta_dev || !partial_dev) return fail(BUMP_E_INVALID, "null theta/partial");
     if (int r = ensure_ready(c)) return r;
-    DeviceChain chain(c->device, static_cast<cudaStream_t>(stream));
+    DeviceChain chain(c, static_cast<cudaStream_t>(stream));
     return launch_partial(c, theta_dev, partial_dev, neff_dev ? neff_dev : c->d_out + OUT_HEADER,
                           static_cast<cudaStream_t>(stream));
 }
@@ -589,7 +607,7 @@ int bump_eval_partial(bump_ctx* c, const double* theta, double* partial, double*
     memcpy(c->h_theta, theta, sizeof(double) * nth);
     CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
     {
-        DeviceChain chain(c->device, c->stream);
+        DeviceChain chain(c, c->stream);
         if (int r = launch_partial(c, c->d_theta, c->d_partial, c->d_out + OUT_HEADER, c->stream)) return r;
     }
     CK(cudaMemcpyAsync(partial, c->d_partial, sizeof(double) * PARTIAL_LEN, cudaMemcpyDeviceToHost, c->stream));
@@ -723,7 +741,7 @@ int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms
     if (stream_ms) {   // the streaming kernel alone: events around each direct launch on the same stream
         float acc = 0.f;
         for (int i = 0; i < iters; ++i) {
-            DeviceChain chain(c->device, c->stream);
+            DeviceChain chain(c, c->stream);
             if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, c->ev0, c->ev1)) return r;
             CK(cudaEventSynchronize(c->ev1));
             float ms = 0.f;

@@ -32,7 +32,11 @@ constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far b
 // The theta-dependent scalars of the current evaluation, copied device-to-device from the table blob right before
 // the launch: FP64 instructions take c[bank][offset] operands directly, so a scalar costs neither a shared-memory
 // load nor a register.  One evaluation at a time per device (bump_lib.cu chains launches through an event).
-__constant__ double K_SC[NSCAL];
+// NSLOT copies, one per constant SLOT: a context is bound to a slot at creation and the kernels are instantiated per
+// slot, so evaluations of up to NSLOT contexts (parallel NUTS chains on a small catalog) overlap on one device.
+constexpr int NSLOT = 4;
+__constant__ double K_SC4[NSLOT][NSCAL];
+#define K_SC K_SC4[SLOT]   // inside templates with an `int SLOT` parameter
 
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +108,7 @@ constexpr int CTAN_BYTES = OFF_CTAN * 8;
 constexpr int SRCH_BYTES = OFF_SRCH * 8;
 
 // `sb` = shared-window address of the table blob
+template <int SLOT>
 __device__ __forceinline__ void mass_eval(const double m, const double lm, const uint32_t sb, MassEval& o) {
     // -(m - M)/(0.05 M) = 20 - m/(0.05 M): one FMA
     const double e = fexp<false>(fma(m, -K_SC[S_INV_DM], 1.0 / TURNON_WIDTH), sb);
@@ -134,6 +139,7 @@ __device__ __forceinline__ void mass_tangents(const MassEval& o, const double wP
     }
 }
 
+template <int SLOT>
 __device__ __forceinline__ double mass_features(const MassEval& o, const double wp, double* __restrict__ a) {
     const double wQ = wp * o.EQ, wP = wp * o.EP;
     a[2 + F_SQ] += wQ;
@@ -150,7 +156,7 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
 // Fixed-cosmology variant (the reference's `pop_model`, intensity_models.py:313-355): the sample carries source-frame
 // (m1, q) and log1p(z) directly, `lpd` = log pdraw - log dVdzdt(z) was folded at upload, and there is no d_L
 // inversion, no Jacobian and no cosmological gradient.
-template <bool WA, class Mid>
+template <int SLOT, bool WA, class Mid>
 __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
                                                   const double lq, const double l1q, const double lpd,
                                                   const uint32_t sb, ThreadAcc& A, Mid&& mid) {
@@ -176,15 +182,15 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
     const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb);
     const double sr = frcp(1.0 + r);
     MassEval M1, M2;
-    mass_eval(m1, lm1, sb, M1);
-    mass_eval(m2, lm2, sb, M2);
+    mass_eval<SLOT>(m1, lm1, sb, M1);
+    mass_eval<SLOT>(m2, lm2, sb, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     const double base = sr * E;
     const double p = (sum1 * sum2) * base;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    mass_features(M1, sum2 * base, A.a);
-    mass_features(M2, sum1 * base, A.a);
+    mass_features<SLOT>(M1, sum2 * base, A.a);
+    mass_features<SLOT>(M2, sum1 * base, A.a);
     const double psig = p * (r * sr);
     A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
@@ -195,7 +201,7 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
 // `mid()` runs once every input of the sample has been consumed (used by the caller to issue the next loads there:
 // issuing them earlier makes the first use of THIS sample's inputs wait on a scoreboard slot shared with the fresh
 // loads, i.e. on a full L2 round trip).
-template <bool WA, class Mid>
+template <int SLOT, bool WA, class Mid>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
                                             const uint32_t sb, ThreadAcc& A, Mid&& mid) {
@@ -259,8 +265,8 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double sig = r * sr;
     // ---- mass function at both masses
     MassEval M1, M2;
-    mass_eval(m1, lm1, sb, M1);
-    mass_eval(m2, lm2, sb, M2);
+    mass_eval<SLOT>(m1, lm1, sb, M1);
+    mass_eval<SLOT>(m2, lm2, sb, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     // ---- the weight and its partial products
     const double base = (sr * iddl) * E;            // everything but the masses and dVc/dz
@@ -269,7 +275,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double bv = base * dvc;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    const double md = mass_features(M1, sum2 * bv, A.a) + mass_features(M2, sum1 * bv, A.a);
+    const double md = mass_features<SLOT>(M1, sum2 * bv, A.a) + mass_features<SLOT>(M2, sum1 * bv, A.a);
     // ---- d w / d t at fixed tables (times p), then the cosmological tangents
     const double lt = zeps * u1;                    // d log1p(z) / dt
     const double psig = p * sig;
@@ -331,7 +337,7 @@ __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ ou
 #else
 #define BUMP_STREAM_BOUNDS __launch_bounds__(STREAM_THREADS, 1)
 #endif
-template <bool WA, bool FIXED>
+template <bool WA, bool FIXED, int SLOT>
 __global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part) {
@@ -396,8 +402,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32);
         auto nothing = [] {};
-        if constexpr (FIXED) eval_sample_fixed<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
-        else eval_sample<WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
+        else eval_sample<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
         // consumed), and the block after it is pulled towards L2 (28 lines: one per lane)
         int e_next = e, k_next = k + 1;
@@ -414,8 +420,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
             }
         };
-        if constexpr (FIXED) eval_sample_fixed<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
-        else eval_sample<WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
+        else eval_sample<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);
@@ -424,5 +430,7 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         k = k_next;
     }
 }
+
+#undef K_SC
 
 }  // namespace bump

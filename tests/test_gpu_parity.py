@@ -311,3 +311,32 @@ def test_sampler_potential_fast_path_matches_evaluate(golden_dir):
             fd = (model.potential(up)[0] - model.potential(um)[0]) / 2e-6
             assert abs(fd - grad[i]) <= 1e-5 * max(1.0, abs(fd))
     model.close()
+
+
+def test_concurrent_contexts_on_one_device_do_not_interfere(golden_dir, hl):
+    """Parallel NUTS chains: one context per chain, each bound to its own constant-bank slot (4 per device), evaluated
+    from concurrent host threads with different theta.  Every result must be bitwise what the same context returns
+    alone; six contexts also cover two of them sharing a slot (those are chained, not overlapped)."""
+    import threading
+    g = _load(golden_dir, "small")
+    thetas = g["thetas"]
+    likes = [hl(*_data(g)) for _ in range(6)]
+    alone = [likes[i].raw(thetas[i % len(thetas)]).copy() for i in range(len(likes))]
+    errors = []
+
+    def work(i):
+        th = thetas[i % len(thetas)]
+        for _ in range(200):
+            out = likes[i].raw(th)
+            if not np.array_equal(out, alone[i], equal_nan=True):
+                errors.append(i)
+                return
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(likes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for like in likes:
+        like.close()
+    assert not errors, f"contexts {sorted(set(errors))} saw another context's parameters"
