@@ -31,18 +31,18 @@ def _stale(target, sources):
 
 
 def sources():
-    src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".cpp"))]
     src.append(os.path.join(os.path.dirname(PKG), "include", "bump.h"))
     return src
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/bump_lib.cu -> libbump_b200.so and csrc/bump_peak.cu -> bump_peak (fp64 issue-rate probe)."""
+    """Compile csrc/bump_lib.cu + csrc/bump_nuts.cpp -> libbump_b200.so and csrc/bump_peak.cu -> bump_peak (fp64 issue-rate probe)."""
     nvcc = _nvcc()
     src = sources()
     if force or _stale(LIB, src):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-            ["-shared", "-o", LIB, os.path.join(CSRC, "bump_lib.cu"), "-ldl"]
+            ["-shared", "-o", LIB, os.path.join(CSRC, "bump_lib.cu"), os.path.join(CSRC, "bump_nuts.cpp"), "-ldl"]
         subprocess.run(cmd, check=True)
     peak_src = os.path.join(CSRC, "bump_peak.cu")
     if os.path.exists(peak_src) and (force or _stale(PEAK, [peak_src])):

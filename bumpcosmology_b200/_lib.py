@@ -46,7 +46,14 @@ SIGNATURES = {
     "bump_time_evals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bump_launches_per_eval": (C.c_int, [C.c_void_p]),
     "bump_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "bump_ctx_flags": (C.c_int, [C.c_void_p]),
+    "bump_nuts_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int, _dp, _dp,
+                                  _dp, _dp, _dp, _dp, _dp]),
+    "bump_nuts_chain_cb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                     C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp]),
 }
+NUTS_NSTAT, NUTS_NDET = 5, 8
+POTENTIAL_CB = C.CFUNCTYPE(C.c_double, C.c_void_p, _dp, _dp)   # double (*)(void* user, const double* u, double* grad)
 
 _lib = None
 

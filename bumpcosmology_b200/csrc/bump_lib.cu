@@ -754,6 +754,10 @@ int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms
     return BUMP_OK;
 }
 
+int bump_ctx_flags(const bump_ctx* c) { return c ? (int)c->flags : -1; }
+
+int bump_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }   // for bump_nuts.cpp
+
 int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 5 : 4) : 0; }
 
 int bump_plan_info(bump_ctx* c, int64_t* info8) {

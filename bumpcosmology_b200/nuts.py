@@ -257,15 +257,84 @@ def run_chain(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
             "warmup_s": (t_warm or t_end) - t_start, "sampling_s": t_end - (t_warm or t_end)}
 
 
-def run_mcmc(model, num_warmup=1000, num_samples=1000, num_chains=4, seed=1652819403, **kw):
+# ------------------------------------------------------------------ the same driver in C++ (csrc/bump_nuts.cpp)
+_STAT_NAMES = ("accept", "depth", "n_leapfrog", "diverging", "potential")
+_DET_NAMES = ("loglike", "selfactor", "neff_sel", "R", "mbhmax", "fpl", "kappa", "neff_min")
+
+
+def _native_result(dim, num_samples, u, x, stats, det, info, minv):
+    return {"u": u, "x": x, "stats": {k: stats[:, i].copy() for i, k in enumerate(_STAT_NAMES)},
+            "deterministic": {k: det[:, i].copy() for i, k in enumerate(_DET_NAMES)},
+            "step_size": float(info[0]), "inverse_mass": minv, "n_leapfrog_total": int(info[1]),
+            "warmup_s": float(info[2]), "sampling_s": float(info[3]), "n_evals": int(info[4])}
+
+
+def run_chain_native(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True, target_accept=0.8,
+                     max_tree_depth=10, init=None, progress=None):
+    """One chain run by the library's C++ driver (`bump_nuts_chain`): same algorithm as `run_chain`, no interpreter in
+    the leapfrog loop.  `model` is a bound `pop_cosmo_model` (single-rank context).  The call releases the GIL, so
+    chains started from several Python threads run truly in parallel."""
+    from . import _lib, priors
+    ctx = getattr(getattr(model, "like", None), "_ctx", None)   # ShardedHyperlikelihood has none: every rank would
+    # have to take the same steps in lock step, which the Python driver does through the merged potential
+    if ctx is None:
+        raise TypeError("run_chain_native needs a model bound to a single-rank Hyperlikelihood")
+    lib = _lib.load()
+    d = priors.NSITES
+    u = np.empty((num_samples, d))
+    x = np.empty((num_samples, d))
+    stats = np.empty((num_samples, _lib.NUTS_NSTAT))
+    det = np.empty((num_samples, _lib.NUTS_NDET))
+    info = np.zeros(8)
+    minv = np.empty((d, d))
+    init_p = _lib.as_dp(np.ascontiguousarray(init, dtype=np.float64)) if init is not None else None
+    _lib.check(lib.bump_nuts_chain(ctx, num_warmup, num_samples, int(seed) & (2**64 - 1), int(dense_mass),
+                                   float(target_accept), int(max_tree_depth), init_p, _lib.as_dp(u), _lib.as_dp(x),
+                                   _lib.as_dp(stats), _lib.as_dp(det), _lib.as_dp(info), _lib.as_dp(minv)))
+    out = _native_result(d, num_samples, u, x, stats, det, info, minv)
+    if hasattr(model, "n_evals"):
+        model.n_evals += out["n_evals"]
+    return out
+
+
+def run_chain_native_fn(potential_fn, dim, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
+                        target_accept=0.8, max_tree_depth=10, init=None):
+    """The C++ driver on an arbitrary Python potential `u -> (U, grad)` (`bump_nuts_chain_cb`; for tests: the
+    callback re-enters the interpreter on every leapfrog step)."""
+    from . import _lib
+    lib = _lib.load()
+
+    def cb(_user, u_p, g_p):
+        uu = np.ctypeslib.as_array(u_p, shape=(dim,))
+        U, g = potential_fn(uu.copy())[:2]
+        np.ctypeslib.as_array(g_p, shape=(dim,))[:] = g
+        return float(U)
+
+    cfn = _lib.POTENTIAL_CB(cb)
+    u = np.empty((num_samples, dim))
+    stats = np.empty((num_samples, _lib.NUTS_NSTAT))
+    info = np.zeros(8)
+    minv = np.empty((dim, dim))
+    init_p = _lib.as_dp(np.ascontiguousarray(init, dtype=np.float64)) if init is not None else None
+    import ctypes
+    _lib.check(lib.bump_nuts_chain_cb(ctypes.cast(cfn, ctypes.c_void_p), None, dim, num_warmup, num_samples,
+                                      int(seed) & (2**64 - 1), int(dense_mass), float(target_accept),
+                                      int(max_tree_depth), init_p, _lib.as_dp(u), _lib.as_dp(stats), _lib.as_dp(info),
+                                      _lib.as_dp(minv)))
+    return _native_result(dim, num_samples, u, u.copy(), stats, np.zeros((num_samples, _lib.NUTS_NDET)), info, minv)
+
+
+def run_mcmc(model, num_warmup=1000, num_samples=1000, num_chains=4, seed=1652819403, native=False, **kw):
     """The reference's MCMC configuration (run_cosmo_fit.py:17-19,45-46).
 
     `model` is one bound model (chains run one after another on it) or a list of `num_chains` bound models, one per
     chain, which then run concurrently in threads — the reference's chains are parallel too (numpyro pmaps them over
     host devices, run_cosmo_fit.py:1-3).  The C call releases the GIL, so one chain's host work (priors,
     transforms, tree bookkeeping) overlaps the others' GPU evaluations; evaluations of different contexts on one
-    device are serialised by the library."""
+    device overlap as long as they sit on different constant-bank slots (four per device).  `native=True` runs each
+    chain in the library's C++ driver (`run_chain_native`) instead of the Python one."""
     t0 = time.perf_counter()
+    chain_fn = run_chain_native if native else run_chain
     if isinstance(model, (list, tuple)):
         import threading
         models = list(model)
@@ -276,7 +345,7 @@ def run_mcmc(model, num_warmup=1000, num_samples=1000, num_chains=4, seed=165281
 
         def work(c):
             try:
-                chains[c] = run_chain(models[c], num_warmup, num_samples, seed=seed + c, **kw)
+                chains[c] = chain_fn(models[c], num_warmup, num_samples, seed=seed + c, **kw)
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
 
@@ -290,7 +359,7 @@ def run_mcmc(model, num_warmup=1000, num_samples=1000, num_chains=4, seed=165281
         warm = max(c["warmup_s"] for c in chains)
         samp = max(c["sampling_s"] for c in chains)
     else:
-        chains = [run_chain(model, num_warmup, num_samples, seed=seed + c, **kw) for c in range(num_chains)]
+        chains = [chain_fn(model, num_warmup, num_samples, seed=seed + c, **kw) for c in range(num_chains)]
         warm = sum(c["warmup_s"] for c in chains)
         samp = sum(c["sampling_s"] for c in chains)
     x = np.stack([c["x"] for c in chains])                      # [chain, draw, site]

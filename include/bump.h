@@ -147,6 +147,30 @@ int bump_launches_per_eval(const bump_ctx* ctx);
  * per CTA, dynamic shared memory bytes, padded samples resident on this rank, SM count}. */
 int bump_plan_info(bump_ctx* ctx, int64_t* info8);
 
+/* ---- Host NUTS driver.  Replaces what numpyro runs for the reference:
+ * `NUTS(pop_cosmo_model, dense_mass=True)`, `MCMC(num_warmup=1000, num_samples=1000, num_chains=4)` with seed
+ * 1652819403 (run_cosmo_fit.py:17-19,45-49).  One chain per call; run the chains from concurrent host threads, one
+ * context each (contexts of one device evaluate concurrently).  Priors / transforms of the 15 sample sites:
+ * intensity_models.py:281-311,398.  Outputs (row-major, caller-allocated):
+ *   out_u, out_x [num_samples][15]   unconstrained / constrained draws, site order h Om w a b c mpisn dmbhmax sigma
+ *                                    beta log_fpl lam dkappa zp R_unit
+ *   out_stats    [num_samples][BUMP_NUTS_NSTAT]   accept prob, tree depth, leapfrog steps, diverging, potential
+ *   out_det      [num_samples][BUMP_NUTS_NDET]    loglike, selfactor, neff_sel, R, mbhmax, fpl, kappa, min neff
+ *   out_info     [8]   step size, leapfrog steps (total), warm-up seconds, sampling seconds, model evaluations
+ *   out_minv     [15][15]  adapted inverse mass matrix (may be NULL; so may out_x / out_det / init_u) */
+#define BUMP_NUTS_NSTAT 5
+#define BUMP_NUTS_NDET 8
+int bump_nuts_chain(bump_ctx* ctx, int num_warmup, int num_samples, uint64_t seed, int dense_mass, double target_accept,
+                    int max_tree_depth, const double* init_u, double* out_u, double* out_x, double* out_stats,
+                    double* out_det, double* out_info, double* out_minv);
+/* The same sampler on an arbitrary potential U(u) with gradient (dim <= 32): the CPU-testable core. */
+typedef double (*bump_potential_cb)(void* user, const double* u, double* grad);
+int bump_nuts_chain_cb(bump_potential_cb f, void* user, int dim, int num_warmup, int num_samples, uint64_t seed,
+                       int dense_mass, double target_accept, int max_tree_depth, const double* init_u, double* out_u,
+                       double* out_stats, double* out_info, double* out_minv);
+/* The flags the context was created with (-1 for a null context). */
+int bump_ctx_flags(const bump_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ ap.add_argument("--seed", type=int, default=1652819403)   # run_cosmo_fit.py:19
 ap.add_argument("--progress", type=int, default=0)
 ap.add_argument("--out", default="")
 ap.add_argument("--sequential", action="store_true", help="one context, chains one after another")
+ap.add_argument("--native", action="store_true", help="the library's C++ driver (bump_nuts_chain) instead of the Python one")
 a = ap.parse_args()
 cat = make_catalog(a.workload)
 if a.sequential:
@@ -26,7 +27,7 @@ else:   # one context per chain, chains in threads (the reference's chains run i
     models = [im.pop_cosmo_model(*cat.as_args()) for _ in range(a.chains)]
     model = models
 t0 = time.perf_counter()
-r = nuts.run_mcmc(model, a.warmup, a.samples, a.chains, seed=a.seed, progress=a.progress or None)
+r = nuts.run_mcmc(model, a.warmup, a.samples, a.chains, seed=a.seed, progress=a.progress or None, native=a.native)
 wall = time.perf_counter() - t0
 ess = r["ess_bulk"][:14]
 x = r["x"]
@@ -37,7 +38,7 @@ line = {
     "ess_per_s_total": float(ess.min() / wall), "ess_per_s_sampling": float(ess.min() / r["sampling_s"]),
     "rhat_max": float(r["rhat"][:14].max()), "n_leapfrog": int(r["n_leapfrog_total"]),
     "evals_per_s": r["n_leapfrog_total"] / wall, "model_evals": sum(m.n_evals for m in models),
-    "chains_in_parallel": not a.sequential,
+    "chains_in_parallel": not a.sequential, "driver": "c++ (bump_nuts_chain)" if a.native else "python (nuts.py)",
     "divergences": int(sum(c["stats"]["diverging"].sum() for c in r["chains"])),
     "mean_accept": float(np.mean([c["stats"]["accept"].mean() for c in r["chains"]])),
     "mean_depth": float(np.mean([c["stats"]["depth"].mean() for c in r["chains"]])),
