@@ -50,5 +50,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_xla_ffi():
+    """Compile csrc/bump_xla_ffi.cc -> libbump_xla_ffi.so against jaxlib's headers (only where JAX is installed)."""
+    import jaxlib   # ImportError here means: no JAX, no adaptor (the ctypes path does not need it)
+    inc = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+    out = os.path.join(PKG, "libbump_xla_ffi.so")
+    subprocess.run([_nvcc()] + NVCC_FLAGS + ["-shared", "-I", inc, "-o", out, os.path.join(CSRC, "bump_xla_ffi.cc"),
+                                              "-L", PKG, "-l:libbump_b200.so", "-Xlinker", "-rpath=$ORIGIN"], check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--xla-ffi" in sys.argv:
+        print(build_xla_ffi())
