@@ -368,7 +368,7 @@ def main():
         # register operands, +1 per other instruction, per warp-sample and sub-partition (4 per SM)
         cyc_model = 2 * EXEC_FP64_INST_PER_SAMPLE + EXEC_FP64_3REG_PER_SAMPLE + EXEC_OTHER_INST_PER_SAMPLE
         sms = pk.get("sms", 148)
-        clk = pk.get("max_clock_mhz", 1965) * 1e6
+        clk = ((clocks or {}).get("sm_mhz") or pk.get("max_clock_mhz", 1965)) * 1e6   # SM clock sampled under load
         cyc_meas = ker_ms * 1e-3 * clk * sms * 4 / (n_local / 32)
         fp64["issue_model"] = {"cycles_per_warp_sample": cyc_model, "measured_cycles_per_warp_sample": cyc_meas,
                                "frac": cyc_model / cyc_meas,

@@ -209,7 +209,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     // The bucket table, keyed by the top bits of x, gives a lower bound b0 of the bin.  A bucket (1/256 octave) is
     // narrower than any bin of the d_L grid (log dl_{k+1} - log dl_k >= ZSTEP = 0.0045 > log(1 + 1/256)), so the
     // bin is b0 or b0 + 1: one comparison with knot b0 + 1, no loop.  (records_kernel flags the evaluation as bad
-    // if theta is so extreme that the ends of the bucket range break this: h > 3.4 or h < 0.05.)
+    // if theta is so extreme that the ends of the bucket range break this: roughly h > 7 or h < 0.11; the prior is 0.35 .. 1.4.)
     int j = (__double2hiint(x) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
     j = min(max(j, 0), SRCH_N - 1);
     const uint32_t b0 = lds16<SRCH_BYTES>(sb + 2u * (uint32_t)j);

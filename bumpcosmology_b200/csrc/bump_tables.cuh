@@ -374,7 +374,7 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
             // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
             // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
             // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
-            // last two bins).  That takes h > 3.4 or h < 0.05, far outside the prior: flag it (-> NaN outputs).
+            // last two bins).  That takes roughly h > 7 or h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).
             const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
             const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
             if (!ec.fixed && (!(aux[AUX_DL + 2] >= first_hi) || !(aux[AUX_DL + NZ - 3] <= last_lo))) *flags = 1u;

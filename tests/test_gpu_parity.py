@@ -344,13 +344,13 @@ def test_concurrent_contexts_on_one_device_do_not_interfere(golden_dir, hl):
 
 def test_hubble_far_outside_the_prior_is_flagged_or_exact(hl):
     """The single-step d_L bin search is exact while the clamped end buckets of the search table hold at most two
-    bins, i.e. for 0.05 < h < 3.4 (prior support: 0.35 .. 1.4).  Inside that range the result must still match the
+    bins, i.e. for roughly 0.11 < h < 7 (prior support: 0.35 .. 1.4).  Inside that range the result must still match the
     oracle; beyond it the evaluation is flagged (NaN), never silently wrong."""
     from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
     from oracle import bump_oracle as bo
     cat = make_catalog("tiny")
     like = hl(*cat.as_args())
-    for h in (0.08, 2.5):
+    for h in (0.15, 5.0):
         th = THETA_DEFAULT.copy()
         th[0] = h
         r = like(th)
@@ -358,7 +358,7 @@ def test_hubble_far_outside_the_prior_is_flagged_or_exact(hl):
         assert _close(r.log_mu_sel, o["log_mu_sel"]) and _close(r.dlog_mu_sel, o["dlog_mu_sel"]), h
         if np.isfinite(o["loglike"]):
             assert _close(r.loglike, o["loglike"]), h
-    for h in (0.01, 10.0):
+    for h in (0.02, 20.0):
         th = THETA_DEFAULT.copy()
         th[0] = h
         assert np.isnan(like(th).log_mu_sel), h
