@@ -506,6 +506,16 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         c->slot = g_dev_next_slot[device]++ % NSLOT;
     }
     CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    {
+        // every kernel of an evaluation asks for the shared-memory carve-out the streaming kernel needs: an SM does not
+        // have to drain and re-partition L1 / shared memory between the four launches (GWTC-3 shape: 56.8 -> 55.3 us per evaluation)
+        const int co = cudaSharedmemCarveoutMaxShared;
+        CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(records_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+    }
     *out = c;
     return BUMP_OK;
 }
