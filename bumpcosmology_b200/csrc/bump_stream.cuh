@@ -1,4 +1,5 @@
-// The streaming kernel: one pass over the SoA sample / injection columns producing, per (warp, event) record, the shifted sums
+// The streaming kernel: one pass over the group-blocked sample / injection columns producing, per (warp, event) record,
+// the shifted sums
 //   S = sum e^{w-m},  S2 = sum e^{2(w-m)}  and the 17 gradient features  sum e^{w-m} f_k.
 //
 // Replaces intensity_models.py:378-381 (events) and :385-388 (injections) — z_of_dL, detector->source masses,
@@ -13,6 +14,12 @@
 // The shift m is per thread: the `lin` of its first finite-weight sample, raised only when a later sample
 // exceeds it by e^RESCALE_GAP (fp64 has the range to carry everything else); lanes, records and ranks are merged
 // with the usual (max, rescale) rule, so the result equals the reference's max-shifted logsumexp.
+//
+// What bounds it (profiles/r01_fp64_issue_microbench.txt): the issue port.  On B200 an FP64
+// instruction occupies its sub-partition for max(2, distinct vector-register operands) cycles and nothing co-issues
+// beside it, so the code below is written to minimise instruction COUNT: constants come from the constant bank
+// (K_SC, K_EXP), table addresses are base register + immediate (lds64/lds128<OFF>), loads carry no predicate (whole
+// groups, blocked layout), and the math is folded into single FMAs wherever two constants do not collide.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -31,7 +38,7 @@ constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far b
 
 // The theta-dependent scalars of the current evaluation, copied device-to-device from the table blob right before
 // the launch: FP64 instructions take c[bank][offset] operands directly, so a scalar costs neither a shared-memory
-// load nor a register.  One evaluation at a time per device (bump_lib.cu chains launches through an event).
+// load nor a register.  One evaluation at a time per slot (bump_lib.cu chains launches through an event).
 // NSLOT copies, one per constant SLOT: a context is bound to a slot at creation and the kernels are instantiated per
 // slot, so evaluations of up to NSLOT contexts (parallel NUTS chains on a small catalog) overlap on one device.
 constexpr int NSLOT = 4;
