@@ -47,12 +47,24 @@ constexpr int NEXPT = 2048;  // 2^(j/2048) (bump_math.cuh fexp); theta-independe
 constexpr int OFF_SCAL = 0;
 constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT]
 constexpr int OFF_COS = OFF_EXPT + NEXPT;               // double2 cos[NCPAIR][NZ]
-constexpr int OFF_CTAN = OFF_COS + NCPAIR * NZ * 2;     // double  ctan[NCTAN][NZ]
-constexpr int OFF_SRCH = OFF_CTAN + NCTAN * NZ;         // uint16  srch[SRCH_N]
+constexpr int OFF_SRCH = OFF_COS + NCPAIR * NZ * 2;     // uint16  srch[SRCH_N]
 constexpr int OFF_MASS = OFF_SRCH + SRCH_DOUBLES;       // double2 mass[NMREC][NM]
-constexpr int BLOB_DOUBLES = OFF_MASS + NMREC * NM * 2;
-constexpr int BLOB_BYTES = BLOB_DOUBLES * 8;
-static_assert(BLOB_BYTES % 16 == 0, "bulk copies need 16-byte multiples");
+// The cosmology tangent tables come last because their format depends on the mode (227 KB of shared memory do not
+// hold nine pair tables):
+//   default (h, Om, w):  double2 ctan2[6][NZ]  per-bin pairs {t_b, t_{b+1} - t_b}: one LDS.128 and no subtraction per lerp
+//   w0-wa             :  double  ctan[9][NZ]   knot values (two LDS.64 and one DADD per lerp)
+//   fixed cosmology   :  none (pop_model has no cosmological gradient)
+constexpr int OFF_CTAN = OFF_MASS + NMREC * NM * 2;
+constexpr int NCTAN_PAIR = 6;
+__host__ __device__ constexpr int blob_doubles(const bool wa, const bool fixed) {
+    return OFF_CTAN + (fixed ? 0 : wa ? NCTAN * NZ : NCTAN_PAIR * NZ * 2);
+}
+constexpr int BLOB_DOUBLES_MAX = OFF_CTAN + NCTAN_PAIR * NZ * 2;
+constexpr int BLOB_BYTES_MAX = BLOB_DOUBLES_MAX * 8;
+static_assert(blob_doubles(true, false) <= BLOB_DOUBLES_MAX, "the pair layout is the largest blob");
+static_assert(BLOB_BYTES_MAX + 16 <= 227 * 1024, "the blob (+ mbarrier) must fit the 227 KB of shared memory per CTA");
+static_assert(OFF_CTAN % 2 == 0 && (blob_doubles(false, false) % 2) == 0 && (blob_doubles(true, false) % 2) == 0,
+              "bulk copies need 16-byte multiples");
 static_assert(SRCH_N % 4 == 0, "search table must fill whole doubles");
 static_assert(OFF_EXPT % 16 == 0, "the exp table must sit on a 128-byte boundary");
 static_assert((NEXPT & (NEXPT - 1)) == 0, "the exp table size is a power of two");

@@ -363,7 +363,7 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                                sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0)
-        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, STREAM_SMEM_BYTES, s>>>(columns_of(c), c->work, c->d_rec_off,
+        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, stream_smem_bytes(c->use_wa, c->fixed), s>>>(columns_of(c), c->work, c->d_rec_off,
                                                                                   c->d_blob, c->d_part);
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
@@ -486,8 +486,8 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaMemset(c->d_theta, 0, sizeof(double) * NTHETA_MAX));
     CK(cudaMalloc(&c->d_aux, sizeof(double) * (AUX_DOUBLES + AUX_CHAIN_DOUBLES)));
-    CK(cudaMalloc(&c->d_blob, BLOB_BYTES));
-    CK(cudaMemset(c->d_blob, 0, BLOB_BYTES));
+    CK(cudaMalloc(&c->d_blob, BLOB_BYTES_MAX));
+    CK(cudaMemset(c->d_blob, 0, BLOB_BYTES_MAX));
     {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
         std::vector<double> expt(NEXPT);
         for (int j = 0; j < NEXPT; ++j) expt[j] = (double)exp2l((long double)j / NEXPT);
@@ -505,7 +505,8 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         std::lock_guard<std::mutex> lk(g_dev_mutex);
         c->slot = g_dev_next_slot[device]++ % NSLOT;
     }
-    CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            stream_smem_bytes(c->use_wa, c->fixed)));
     {
         // every kernel of an evaluation asks for the shared-memory carve-out the streaming kernel needs: an SM does not
         // have to drain and re-partition L1 / shared memory between the four launches (GWTC-3 shape: 56.8 -> 55.3 us per evaluation)
@@ -778,7 +779,7 @@ int bump_plan_info(bump_ctx* c, int64_t* info8) {
     info8[2] = c->nrecords;
     info8[3] = c->grid;
     info8[4] = STREAM_THREADS;
-    info8[5] = STREAM_SMEM_BYTES;
+    info8[5] = stream_smem_bytes(c->use_wa, c->fixed);
     info8[6] = c->evt.nrows * c->evt.stride + c->sel.nrows * c->sel.stride;
     info8[7] = c->sm_count;
     return BUMP_OK;

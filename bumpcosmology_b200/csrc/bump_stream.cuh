@@ -33,7 +33,9 @@ namespace bump {
 #endif
 constexpr int STREAM_THREADS = BUMP_STREAM_THREADS;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
-constexpr int STREAM_SMEM_BYTES = BLOB_BYTES + 16 /*mbarrier*/;
+__host__ __device__ constexpr int stream_smem_bytes(const bool wa, const bool fixed) {
+    return blob_doubles(wa, fixed) * 8 + 16 /*mbarrier*/;
+}
 constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
 // The theta-dependent scalars of the current evaluation, copied device-to-device from the table blob right before
@@ -48,6 +50,7 @@ __constant__ double K_SC4[NSLOT][NSCAL];
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <int BLOB_BYTES>
 __device__ __forceinline__ void stage_tables(double* s_blob, uint64_t* mbar, const double* __restrict__ g_blob) {
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -223,7 +226,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double knot = lds64<COS_BYTES + CR_DL * NZ * 16 + 16>(sb + 16u * b0);   // dl[b0 + 1]
     const uint32_t b = min(b0 + (x >= knot ? 1u : 0u), (uint32_t)(NZ - 2));
     const uint32_t ab = sb + 16u * b;   // the bin's pair records
-    const uint32_t at = sb + 8u * b;    // the bin's tangent-table knots
+    const uint32_t at = sb + 8u * b;    // the bin's tangent-table knots (w0-wa mode)
     const double2 rdl = lds128<COS_BYTES + CR_DL * NZ * 16>(ab);
     const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     double t = (x - rdl.x) * rdl.y;
@@ -291,12 +294,19 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     A.a[2 + F_CZ] = fma(pWx, x, A.a[2 + F_CZ]);
     const double pid = p * iddl;
     auto tangent = [&](auto tdl, auto tdvc, auto tddl, double& acc) {
-        constexpr int ODL = CTAN_BYTES + decltype(tdl)::value * NZ * 8, ODVC = CTAN_BYTES + decltype(tdvc)::value * NZ * 8,
-                      ODDL = CTAN_BYTES + decltype(tddl)::value * NZ * 8;
-        const double a0 = lds64<ODL>(at), a1 = lds64<ODL + 8>(at);
-        const double v0 = lds64<ODVC>(at), v1 = lds64<ODVC + 8>(at);
-        const double d0 = lds64<ODDL>(at), d1 = lds64<ODDL + 8>(at);
-        acc = fma(-pWx, fma(t, a1 - a0, a0), fma(p0, fma(t, v1 - v0, v0), fma(-pid, fma(t, d1 - d0, d0), acc)));
+        if constexpr (WA) {   // knot values
+            constexpr int ODL = CTAN_BYTES + decltype(tdl)::value * NZ * 8, ODVC = CTAN_BYTES + decltype(tdvc)::value * NZ * 8,
+                          ODDL = CTAN_BYTES + decltype(tddl)::value * NZ * 8;
+            const double a0 = lds64<ODL>(at), a1 = lds64<ODL + 8>(at);
+            const double v0 = lds64<ODVC>(at), v1 = lds64<ODVC + 8>(at);
+            const double d0 = lds64<ODDL>(at), d1 = lds64<ODDL + 8>(at);
+            acc = fma(-pWx, fma(t, a1 - a0, a0), fma(p0, fma(t, v1 - v0, v0), fma(-pid, fma(t, d1 - d0, d0), acc)));
+        } else {              // per-bin pairs {t_b, t_{b+1} - t_b}
+            const double2 a = lds128<CTAN_BYTES + decltype(tdl)::value * NZ * 16>(ab);
+            const double2 v = lds128<CTAN_BYTES + decltype(tdvc)::value * NZ * 16>(ab);
+            const double2 d = lds128<CTAN_BYTES + decltype(tddl)::value * NZ * 16>(ab);
+            acc = fma(-pWx, fma(t, a.y, a.x), fma(p0, fma(t, v.y, v.x), fma(-pid, fma(t, d.y, d.x), acc)));
+        }
     };
     tangent(IC<CT_DL_OM>{}, IC<CT_DVC_OM>{}, IC<CT_DDL_OM>{}, A.a[2 + F_OM]);
     tangent(IC<CT_DL_W>{}, IC<CT_DVC_W>{}, IC<CT_DDL_W>{}, A.a[2 + F_W]);
@@ -349,10 +359,11 @@ __global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int BLOB_BYTES = blob_doubles(WA, FIXED) * 8;   // the mode's share of the blob (bump_layout.cuh)
     double* s_blob = reinterpret_cast<double*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + BLOB_BYTES);
 
-    stage_tables(s_blob, mbar, g_blob);
+    stage_tables<BLOB_BYTES>(s_blob, mbar, g_blob);
     // shared-window address of the blob, laundered so that it lives in one register for the whole kernel (the
     // compiler otherwise rematerialises it - S2R, MOV, LEA - in front of every table access)
     uint32_t sb = smem_u32(smem_raw);

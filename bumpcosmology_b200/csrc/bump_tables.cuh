@@ -401,10 +401,22 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
         cos[CR_DVC * NZ + b] = make_double2(dvc[b0], dvc[b1] - dvc[b0]);
         cos[CR_DDL * NZ + b] = make_double2(ddl[b0], ddl[b1] - ddl[b0]);
         cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), b0 * ZSTEP);
-        // tangent tables (knot values): aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan
+        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
+        // pairs {t_b, t_{b+1} - t_b} otherwise (bump_layout.cuh), nothing in fixed-cosmology mode
         const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
+        if (ec.fixed) return;
+        if (ec.use_wa) {
 #pragma unroll
-        for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
+            for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
+        } else {
+            double2* ctan2 = reinterpret_cast<double2*>(ctan);
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                if (r % 3 == 2) continue;   // the wa tangents
+                const double* t = aux + AUX_TAN + r * NZ;
+                ctan2[dst[r] * NZ + b] = make_double2(t[b0], t[b1] - t[b0]);
+            }
+        }
         return;
     }
     item -= NZ;
