@@ -34,8 +34,8 @@ ALGO_FP64_INST_PER_SAMPLE = 700      # forward + 14-parameter gr
 # issue cycles its instruction mix needs per warp-sample under the measured B200 issue rules
 # (profiles/r01_fp64_issue_microbench.txt: an FP64 instruction occupies its sub-partition for max(2, distinct
 # vector-register operands) cycles, every other instruction for ~1; nothing hides in the FP64 pipe's second cycle).
-EXEC_FP64_INST_PER_SAMPLE = 223.5
-EXEC_OTHER_INST_PER_SAMPLE = 189.2
+EXEC_FP64_INST_PER_SAMPLE = 217.5
+EXEC_OTHER_INST_PER_SAMPLE = 182.4
 EXEC_FP64_3REG_PER_SAMPLE = 86.5
 DRAM_BYTES_PER_SAMPLE = 56.3
 
@@ -363,7 +363,7 @@ def main():
                 "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE, "algorithmic_frac": algo / pk["dfma_per_s"],
                 "note": "frac = FP64-pipe instructions the kernel executes (ncu, profiles/) x samples / kernel time, "
                         "over the DFMA issue rate measured by bump_peak in this run; algorithmic_frac uses SURVEY.md "
-                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 3.1x fewer"}
+                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 3.2x fewer"}
         # issue ceiling of this instruction mix: 2 cycles per FP64 instruction, +1 for each with three distinct
         # register operands, +1 per other instruction, per warp-sample and sub-partition (4 per SM)
         cyc_model = 2 * EXEC_FP64_INST_PER_SAMPLE + EXEC_FP64_3REG_PER_SAMPLE + EXEC_OTHER_INST_PER_SAMPLE
