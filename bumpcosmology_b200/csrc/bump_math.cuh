@@ -75,7 +75,8 @@ __device__ __forceinline__ double fexp(const double x, const uint32_t sb) {
     p *= r;
     const double T = lds64<OFF_EXPT * 8>(sb + ((uint32_t)(n & (NEXPT - 1)) << 3));
     const double v = fma(T, p, T);
-    const int hi = (max(n, -1010 * NEXPT) & ~(NEXPT - 1)) * 512 + __double2hiint(v);   // + ((n >> 11) << 20): one IMAD
+    int hi;   // hi word of v + ((n >> 11) << 20), as ONE integer multiply-add (ptxas otherwise emits shift + add)
+    asm("mad.lo.s32 %0, %1, 512, %2;" : "=r"(hi) : "r"(max(n, -1010 * NEXPT) & ~(NEXPT - 1)), "r"(__double2hiint(v)));
     return __hiloint2double(hi, __double2loint(v));
 }
 static_assert(NEXPT == 2048, "fexp's constants assume a 2048-entry table");
