@@ -77,3 +77,26 @@ def test_native_nuts_divergent_potential_is_flagged_not_fatal():
     c = nuts.run_chain_native_fn(funnel, 2, num_warmup=100, num_samples=200, seed=1, init=np.zeros(2))
     assert np.all(np.abs(c["u"]) <= 3.0)
     assert np.all(np.isfinite(c["stats"]["potential"]))
+
+
+def test_native_nuts_is_reproducible_and_validates_arguments():
+    mu, cov, f = _gaussian(dim=4, seed=9)
+    a = nuts.run_chain_native_fn(f, 4, num_warmup=80, num_samples=60, seed=42)
+    b = nuts.run_chain_native_fn(f, 4, num_warmup=80, num_samples=60, seed=42)
+    c = nuts.run_chain_native_fn(f, 4, num_warmup=80, num_samples=60, seed=43)
+    assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["stats"]["depth"], b["stats"]["depth"])
+    assert not np.array_equal(a["u"], c["u"])
+    from bumpcosmology_b200._lib import BumpError
+    import pytest
+    with pytest.raises(BumpError, match="dimension"):
+        nuts.run_chain_native_fn(lambda u: (0.0, np.zeros(40)), 40, num_warmup=5, num_samples=5)
+    with pytest.raises(BumpError, match="finite starting point"):
+        nuts.run_chain_native_fn(lambda u: (float("nan"), np.zeros(2)), 2, num_warmup=5, num_samples=5)
+
+
+def test_native_nuts_diagonal_mass_matrix_option():
+    mu, cov, f = _gaussian(dim=5, seed=2)
+    c = nuts.run_chain_native_fn(f, 5, num_warmup=200, num_samples=200, seed=3, dense_mass=False)
+    m = c["inverse_mass"]
+    assert np.allclose(m, np.diag(np.diag(m)))
+    assert np.all(np.abs(c["u"].mean(0) - mu) < 0.4 * np.sqrt(np.diag(cov)))
