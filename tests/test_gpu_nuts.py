@@ -43,3 +43,30 @@ def test_native_and_python_chains_agree_statistically(model):
     sd = b["x"].std(0)
     # two independent chains of ~300 correlated draws each: means within a generous multiple of the spread
     assert np.all(np.abs(a["x"].mean(0) - b["x"].mean(0)) < 0.6 * sd)
+
+
+def test_fit_driver_end_to_end_from_tables(tmp_path):
+    """The reference's run_cosmo_fit.py flow on mock tables: tables -> detector frame -> 2 chains of the C++ driver ->
+    trace file with the reference's site and deterministic names."""
+    import pandas as pd
+
+    from bumpcosmology_b200 import priors, run_cosmo_fit
+    from mock_tables import make_tables
+    pe, sel = make_tables()
+    pd.DataFrame(pe).to_parquet(tmp_path / "pe-samples.parquet")
+    pd.DataFrame(sel).to_parquet(tmp_path / "selection-samples.parquet")
+    out = tmp_path / "trace_cosmo.npz"
+    trace = run_cosmo_fit.main(["--pe", str(tmp_path / "pe-samples.parquet"), "--sel",
+                                str(tmp_path / "selection-samples.parquet"), "--out", str(out), "--nmcmc", "120",
+                                "--nchain", "2"])
+    z = np.load(out)
+    assert list(z["site_names"]) == list(priors.SITE_NAMES)
+    assert z["posterior"].shape == (2, 120, 15) and np.all(np.isfinite(z["posterior"]))
+    for k in ("det_loglike", "det_selfactor", "det_neff_sel", "det_R", "det_mbhmax", "det_fpl", "det_kappa",
+              "stat_accept", "stat_depth", "stat_diverging"):
+        assert z[k].shape == (2, 120), k
+    x = z["posterior"]
+    names = list(z["site_names"])
+    assert np.allclose(z["det_mbhmax"], x[:, :, names.index("mpisn")] + x[:, :, names.index("dmbhmax")])
+    assert np.allclose(z["det_fpl"], np.exp(x[:, :, names.index("log_fpl")]))
+    assert 0.5 < trace["stat_accept"].mean() <= 1.0
