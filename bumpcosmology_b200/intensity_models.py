@@ -199,6 +199,35 @@ class PopModel:
 
     __call__ = evaluate
 
+    # ---- potential energy in unconstrained space (12 sites), as numpyro's NUTS sees pop_model
+    dim = len(FIXED_SITES)
+
+    @staticmethod
+    def constrain(u):
+        return priors.constrain(u, priors.FIXED_SITES)
+
+    def potential(self, u):
+        """U(u) = -[log prior + log|dx/du| + loglike + selfactor] and dU/du for the 12 sites of `pop_model`
+        (a, b, c, mpisn, dmbhmax, sigma, beta, log_fpl, lam, dkappa, zp, R_unit); same structure as
+        `PopCosmoModel.potential`."""
+        x, dx, lpj, glp, dlj = priors.potential_terms(u, priors.FIXED_SITES)
+        a, b, c, mpisn, dmbhmax, sigma, beta, log_fpl, lam, dkappa, zp, r_unit = x
+        fpl = math.exp(log_fpl)
+        theta = (0.7, 0.3, -1.0, a, b, c, mpisn, mpisn + dmbhmax, sigma, fpl, beta, lam, lam + dkappa, zp)
+        out = self.like.raw(theta)
+        self.n_evals = getattr(self, "n_evals", 0) + 1
+        nobs = out[36]
+        logl = out[0] - nobs * out[1]
+        rec = (theta, r_unit, out[:40].copy(), out[40:].copy())
+        if not (math.isfinite(logl) and math.isfinite(lpj)):
+            return math.inf, np.zeros(self.dim), rec
+        gt = out[4:18] - nobs * out[19:33]            # d(loglike + selfactor)/d theta; entries 0..2 are zero here
+        g = [gt[3], gt[4], gt[5], gt[6] + gt[7], gt[7], gt[8], gt[10], fpl * gt[9], gt[11] + gt[12], gt[12], gt[13], 0.0]
+        grad = np.array([-((g[i] + glp[i]) * dx[i] + dlj[i]) for i in range(self.dim)])
+        return -(lpj + logl), grad, rec
+
+    deterministics = staticmethod(lambda rec: PopCosmoModel.deterministics(rec))
+
     def close(self):
         self.like.close()
 

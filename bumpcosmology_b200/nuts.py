@@ -201,7 +201,8 @@ def run_chain(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
     """One chain.  `model.potential(u)` -> (U, dU/du, evaluation dict).  Returns a dict of arrays."""
     from . import priors
     rng = np.random.default_rng(seed)
-    dim = priors.NSITES
+    dim = getattr(model, "dim", priors.NSITES)          # pop_cosmo_model: 15 sites; pop_model: 12
+    constrain = getattr(model, "constrain", priors.constrain)
     f = model.potential
     # init like numpyro's init_to_uniform: uniform(-2, 2) in unconstrained space, retried until finite
     for _ in range(100):
@@ -242,7 +243,7 @@ def run_chain(model, num_warmup=1000, num_samples=1000, seed=0, dense_mass=True,
         else:
             j = it - num_warmup
             out_u[j] = u
-            out_x[j] = priors.constrain(u)[0]
+            out_x[j] = constrain(u)[0]
             stats["accept"][j], stats["depth"][j], stats["n_leapfrog"][j] = acc, depth, nlf
             stats["diverging"][j], stats["potential"][j] = div, U
             evd = model.deterministics(ev) if hasattr(model, "deterministics") else ev

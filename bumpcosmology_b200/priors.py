@@ -101,6 +101,7 @@ SITES = (
 )
 SITE_NAMES = tuple(s.name for s in SITES)
 NSITES = len(SITES)              # 15; the first 14 enter the likelihood
+FIXED_SITES = SITES[3:]          # pop_model (fixed cosmology, intensity_models.py:313-355): no h, Om, w
 LIKELIHOOD_SITES = SITE_NAMES[:14]
 
 
@@ -129,19 +130,22 @@ def log_prior(x):
     return lp, g
 
 
-def constrain(u):
-    """Unconstrained vector -> (x, dx/du, sum log|dx/du|, d(sum log|dx/du|)/du)."""
-    x = np.empty(NSITES)
-    dx = np.empty(NSITES)
-    dlj = np.empty(NSITES)
+def constrain(u, sites=None):
+    """Unconstrained vector -> (x, dx/du, sum log|dx/du|, d(sum log|dx/du|)/du).  `sites`: the model's site table
+    (default: the 15 sites of pop_cosmo_model)."""
+    sites = SITES if sites is None else sites
+    n = len(sites)
+    x = np.empty(n)
+    dx = np.empty(n)
+    dlj = np.empty(n)
     lj = 0.0
-    for i, s in enumerate(SITES):
+    for i, s in enumerate(sites):
         x[i], dx[i], l, dlj[i] = s.forward(float(u[i]))
         lj += l
     return x, dx, lj, dlj
 
 
-def potential_terms(u):
+def potential_terms(u, sites=None):
     """One pass over the sites for NUTS: (x, dx/du, log prior + log|dx/du|, d/du of that sum's explicit part).
 
     Equivalent to constrain() followed by log_prior(), fused and kept in plain Python floats (15 scalars: numpy
@@ -150,7 +154,7 @@ def potential_terms(u):
     xs, dxs, glps, dljs = [], [], [], []
     total = 0.0
     exp, log1p, log = math.exp, math.log1p, math.log
-    for s, ui in zip(SITES, u):
+    for s, ui in zip(SITES if sites is None else sites, u):
         ui = float(ui)
         lo, hi = s.lo, s.hi
         if lo != -math.inf and hi != math.inf:

@@ -70,3 +70,41 @@ def test_fit_driver_end_to_end_from_tables(tmp_path):
     assert np.allclose(z["det_mbhmax"], x[:, :, names.index("mpisn")] + x[:, :, names.index("dmbhmax")])
     assert np.allclose(z["det_fpl"], np.exp(x[:, :, names.index("log_fpl")]))
     assert 0.5 < trace["stat_accept"].mean() <= 1.0
+
+
+def test_fixed_cosmology_potential_gradient_and_fit_driver(tmp_path):
+    """pop_model (the reference's run_fit.py path): the 12-site potential's gradient equals central differences, and the
+    fit driver runs end to end from tables with the Python NUTS driver."""
+    import pandas as pd
+
+    from bumpcosmology_b200 import inputs, intensity_models as im, run_fit
+    from mock_tables import make_tables
+    pe, sel = make_tables(nobs=8, nsamp=128, nsel=5000)
+    _, (m1s, qs, zs, wts) = inputs.group_events(pe["evt"], pe["m1"], pe["q"], pe["z"], pe["wt"])
+    model = im.pop_model(m1s, qs, zs, wts, sel["m1"], sel["q"], sel["z"], sel["pdraw"], float(sel["ndraw"][0]),
+                         dVdzdt_interp=inputs.FlatLCDM().dVdzdt_interp())
+    rng = np.random.default_rng(2)
+    u = rng.uniform(-0.5, 0.5, 12)
+    U, g, rec = model.potential(u)
+    assert np.isfinite(U) and g.shape == (12,)
+    for i in range(12):
+        up, um = u.copy(), u.copy()
+        up[i] += 1e-7
+        um[i] -= 1e-7
+        fd = (model.potential(up)[0] - model.potential(um)[0]) / 2e-7
+        # mpisn, dmbhmax and sigma move the knots of the PISN table: a sample crossing a knot between the two
+        # evaluations adds a slope jump to the difference quotient (the analytic gradient is pinned to the reference at
+        # 1e-10 in test_gpu_parity.py; this test is about the chain rule of the 12-site potential)
+        tol = 5e-3 if i in (3, 4, 5) else 2e-5
+        assert abs(fd - g[i]) <= tol * max(1.0, abs(g[i])), (i, fd, g[i])
+    det = model.deterministics(rec)
+    x = model.constrain(u)[0]
+    assert abs(det["mbhmax"] - (x[3] + x[4])) < 1e-12
+    model.close()
+    pd.DataFrame(pe).to_parquet(tmp_path / "pe.parquet")
+    pd.DataFrame(sel).to_parquet(tmp_path / "sel.parquet")
+    trace = run_fit.main(["--pe", str(tmp_path / "pe.parquet"), "--sel", str(tmp_path / "sel.parquet"), "--out",
+                          str(tmp_path / "trace.npz"), "--nmcmc", "60", "--nchain", "2"])
+    assert trace["posterior"].shape == (2, 60, 12) and np.all(np.isfinite(trace["posterior"]))
+    assert list(trace["site_names"]) == list(im.FIXED_SITES)
+    assert 0.05 < trace["stat_accept"].mean() <= 1.0   # 60 warm-up steps: barely adapted
