@@ -4,16 +4,24 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU path (oracle port) on the box's host cores
+    python bench.py --impl reference ...      # the CPU path (oracle port) on the box's host cores, full workload
 
 One "step" = one evaluation of the hot path (theta -> logL parts, both 14-parameter gradients, Neff's) over the
 whole catalog, which is resident in HBM (uploaded once, exactly as the reference's jitted model closes over its
 data; NUTS only ever changes theta).  `value` times K back-to-back evaluations with CUDA events on the stream
 they are launched on; `e2e` times the public host call (host theta in, host result out) by wall clock.
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Besides the headline it carries, all measured in the same run:
+
+  roofline      the streaming kernel against the FP64 pipe (the binding resource) with HBM alongside
+  cpu_baseline  the fused C++/OpenMP port (oracle/bump_cpu.cpp) on the FULL workload, all host cores
+  configs       the other BASELINE.json shapes (GWTC-3, O4, O5 with w0-wa), sharded like the headline
+  nuts          (1 GPU) NUTS 4 x (1000 + 1000), dense mass, the reference's seed, on the GWTC-3 shape: ESS/s
+  result_check  (N > 1) every output of the sharded evaluation against an unsharded evaluation on rank 0's GPU;
+                the process exits non-zero if they differ by more than 1e-12
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,16 +36,20 @@ sys.path.insert(0, ROOT)
 METRIC = "hyperlikelihood logL+grad evals/sec (O5 mock)"
 UNIT = "evals/s"
 ALGO_BYTES_PER_SAMPLE = 32           # m1_det, q, d_L, pdraw as fp64
-ALGO_FP64_INST_PER_SAMPLE = 700      # forward + 14-parameter gradient, FP64-pipe instructions
-# Measured with ncu on the same command (profiles/r01b_o5_stream_kernel_opmix.txt / _ncu.txt): FP64-pipe warp
-# instructions the streaming kernel actually executes per 32 samples, DRAM bytes it reads per (real) sample, and the
-# issue cycles its instruction mix needs per warp-sample under the measured B200 issue rules
-# (profiles/r01_fp64_issue_microbench.txt: an FP64 instruction occupies its sub-partition for max(2, distinct
-# vector-register operands) cycles, every other instruction for ~1; nothing hides in the FP64 pipe's second cycle).
-EXEC_FP64_INST_PER_SAMPLE = 217.5
-EXEC_OTHER_INST_PER_SAMPLE = 182.4
-EXEC_FP64_3REG_PER_SAMPLE = 86.5
-DRAM_BYTES_PER_SAMPLE = 56.3
+# FP64-pipe warp instructions per 32 samples that the hot path needs, FROZEN at what the round-1 streaming kernel
+# executed (ncu, profiles/r01b_o5_stream_kernel_opmix.txt): 8 exp, 4 reciprocals, the table lerps and the 19 shifted
+# sums.  roofline.achieved = this x samples / kernel time, so it rises when the kernel gets faster, whatever the
+# kernel then executes (SURVEY.md 8(d)'s a-priori estimate was 700).
+ALGO_FP64_INST_PER_SAMPLE = 217.5
+FP64_PEAK_FALLBACK = 1.84e13         # DFMA warp-lane instructions/s measured by bump_peak on this pool's B200s
+MULTIRANK_TOL = 1e-12
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class OneLineStdout:
@@ -124,106 +136,178 @@ def workload_catalog(name):
     return cat, time.time() - t0
 
 
-def _sample_of(cat, frac):
-    ne = max(1, int(round(cat.nobs * frac)))
-    ns = max(1, int(round(cat.nsel * frac)))
-    data = (cat.m1s_det[:ne], cat.qs[:ne], cat.dls[:ne], cat.pdraw[:ne], cat.m1s_det_sel[:ns], cat.qs_sel[:ns],
-            cat.dls_sel[:ns], cat.pdraw_sel[:ns], cat.Ndraw)
-    n_sample = ne * cat.nsamp + ns
-    desc = (f"{ne} of {cat.nobs} events x {cat.nsamp} samples + {ns} of {cat.nsel} injections "
-            f"({100 * n_sample / cat.n_elements:.2f}% of the workload's elements)")
-    return data, n_sample / cat.n_elements, desc
+def config_of(args, cat):
+    """Identical in both arms (the driver compares them): what is computed, not how."""
+    return {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections"
+                        + (", w0-wa dark energy (15 parameters)" if args.wa else ""),
+            "elements": cat.n_elements, "outputs": "loglike, log_mu_sel, log_mu2, neff_sel, neff[nobs], "
+                                                   "d loglike/d theta[14], d log_mu_sel/d theta[14]",
+            "l2": "inputs (1.92 GB at O5) exceed the 126 MB L2; every step re-reads them from HBM"
+                  if 32 * cat.n_elements > 2.5e8 else "inputs fit in L2 (NUTS re-reads the same data every step)"}
 
 
-def cpu_port_cpp(cat, frac, evals, warm):
-    """oracle/bump_cpu.cpp: fused single-pass C++/OpenMP port, all host threads.  Returns (evals/s extrapolated
-    linearly to the full workload, per-eval seconds on the sample, sample description, threads) or None."""
+# ------------------------------------------------------------------------------------------------ CPU arm
+def time_cpu_port(cat, steps, warmup):
+    """oracle/bump_cpu.cpp (fused single-pass C++/OpenMP port, -march=native build made on this host) on the FULL
+    workload with every core this process may use.  Returns dict or None (no compiler / library)."""
     try:
         from oracle import bump_cpu
-        data, scale, desc = _sample_of(cat, frac)
-        port = bump_cpu.CpuPort(*data)
-    except Exception as e:  # noqa: BLE001  (no compiler on the box, ...)
+        port = bump_cpu.CpuPort(*cat.as_args(), native=True)
+    except Exception as e:  # noqa: BLE001
         print(f"[bench] C++ CPU port unavailable: {e}", file=sys.stderr)
         return None
     from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas
-    thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(7, seed=5)])
-    for i in range(warm):
-        port.evaluate(thetas[i % len(thetas)])
+    thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(15, seed=5)])
+    threads = host_threads()
+    for i in range(warmup):
+        port.evaluate(thetas[i % len(thetas)], nthreads=threads)
     ts = []
-    for i in range(evals):
+    t_all = time.perf_counter()
+    for i in range(steps):
         t0 = time.perf_counter()
-        port.evaluate(thetas[i % len(thetas)])
+        port.evaluate(thetas[i % len(thetas)], nthreads=threads)
         ts.append(time.perf_counter() - t0)
-    t = float(np.median(ts))
-    threads = port.threads
+    t_all = time.perf_counter() - t_all
+    lib = os.path.basename(bump_cpu.loaded_path or "")
     port.close()
-    return scale / t, t, desc, threads
+    return {"value": steps / t_all, "s_per_eval_median": float(np.median(ts)), "s_total": t_all, "cores": threads,
+            "host_cpus": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+            "engine": f"cpp_openmp (oracle/bump_cpu.cpp: fused single pass, log space, libm; {lib})",
+            "sample": f"the full workload ({cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections), "
+                      f"{steps} evaluations after {warmup} warm-ups, {threads} OpenMP threads set explicitly"}
 
 
-def cpu_port_torch(cat, frac, evals, warm):
-    """oracle/bump_oracle.py: the parity oracle (eager torch fp64 + autograd), all host threads."""
+def time_cpu_torch(cat, evals, warm):
+    """oracle/bump_oracle.py (eager torch fp64 + autograd), bounded sample: only if the C++ port cannot be built."""
     import torch
 
-    from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT
     from oracle import bump_oracle as bo
-    data, scale, desc = _sample_of(cat, frac)
-    thetas = np.vstack([THETA_DEFAULT, draw_prior_thetas(7, seed=5)])
+    torch.set_num_threads(host_threads())
+    frac = min(1.0, 900_000 / cat.n_elements)
+    ne, ns = max(1, int(round(cat.nobs * frac))), max(1, int(round(cat.nsel * frac)))
+    data = (cat.m1s_det[:ne], cat.qs[:ne], cat.dls[:ne], cat.pdraw[:ne], cat.m1s_det_sel[:ns], cat.qs_sel[:ns],
+            cat.dls_sel[:ns], cat.pdraw_sel[:ns], cat.Ndraw)
+    scale = (ne * cat.nsamp + ns) / cat.n_elements
     chunk = max(1, 2_000_000 // max(cat.nsamp, 1))
-    for i in range(warm):
-        bo.evaluate(thetas[i % len(thetas)], data, grad=True, event_chunk=chunk)
-    ts = []
-    for i in range(evals):
-        t0 = time.perf_counter()
-        bo.evaluate(thetas[i % len(thetas)], data, grad=True, event_chunk=chunk)
-        ts.append(time.perf_counter() - t0)
-    t = float(np.median(ts))
-    return scale / t, t, desc, torch.get_num_threads()
+    for _ in range(warm):
+        bo.evaluate(THETA_DEFAULT, data, grad=True, event_chunk=chunk)
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        bo.evaluate(THETA_DEFAULT, data, grad=True, event_chunk=chunk)
+    t = (time.perf_counter() - t0) / evals
+    return {"value": scale / t, "s_per_eval_median": t / scale, "cores": torch.get_num_threads(),
+            "host_cpus": os.cpu_count(), "engine": "torch_eager (oracle/bump_oracle.py)",
+            "sample": f"{ne} events + {ns} injections ({100 * scale:.1f} % of the elements), extrapolated linearly"}
 
 
-def cpu_baseline(cat, evals=8, warm=2):
-    """Both CPU stand-ins for "the reference's JAX on the host cores"  on bounded samples of
-    the workload; the FASTER one is the reported baseline."""
-    out = {}
-    cpp = cpu_port_cpp(cat, min(1.0, 6_000_000 / cat.n_elements), evals, warm)
-    if cpp:
-        out["cpp_openmp"] = {"value": cpp[0], "sample_s_per_eval": cpp[1], "sample": cpp[2], "cores": cpp[3]}
-    tv = cpu_port_torch(cat, min(1.0, 900_000 / cat.n_elements), max(3, evals // 2), 1)
-    out["torch_eager"] = {"value": tv[0], "sample_s_per_eval": tv[1], "sample": tv[2], "cores": tv[3]}
-    best = max(out, key=lambda k: out[k]["value"])
-    b = out[best]
-    return {"value": b["value"], "unit": UNIT, "cores": b["cores"], "kind": "port", "engine": best,
-            "sample": b["sample"] + f", {evals} evals after {warm} warm-ups, median, extrapolated linearly in "
-                                    "element count",
-            "sample_s_per_eval": b["sample_s_per_eval"], "host_cpus": os.cpu_count(), "engines": out}
+def cpu_arm(cat, steps, warmup):
+    r = time_cpu_port(cat, steps, warmup)
+    return r if r is not None else time_cpu_torch(cat, max(2, min(steps, 3)), 1)
 
 
 def run_reference(args, rank, out):
     """The reference arm: the reference's algorithm on the host cores.  The reference itself (JAX/numpyro) is not
-    installable in this image, so this times the faster CPU port of oracle/ (normally the fused C++/OpenMP one)."""
+    installable in this image, so this times the fused C++/OpenMP port of oracle/ on the same config, FULL workload
+    per step, all host cores (set explicitly: torchrun exports OMP_NUM_THREADS=1)."""
     if rank != 0:
         return
     cat, _ = workload_catalog(args.workload)
-    frac = min(1.0, 6_000_000 / cat.n_elements)      # 10 % of O5 per step: the whole arm stays within a few minutes
-    cpp = cpu_port_cpp(cat, frac, args.steps, args.warmup)
-    if cpp:
-        v, t_step, sample, threads = cpp
-        engine = "cpp_openmp (oracle/bump_cpu.cpp: fused single pass, log space, libm)"
-    else:
-        v, t_step, sample, threads = cpu_port_torch(cat, min(1.0, 900_000 / cat.n_elements), args.steps, args.warmup)
-        engine = "torch_eager (oracle/bump_oracle.py)"
+    r = cpu_arm(cat, args.steps, args.warmup)
+    v = r["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections",
-                   "note": "reference JAX stack is not installable here; CPU arm = " + engine + ", all host threads; "
-                           "each step is one logL+grad evaluation of a bounded sample, extrapolated linearly"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "sample_s_per_eval": t_step, "host_cpus": os.cpu_count(), "engine": engine},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, cat),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "s_per_eval_median": r["s_per_eval_median"], "host_cpus": r["host_cpus"],
+                         "engine": r["engine"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "reference JAX stack is not installable here (no wheel, no network); CPU arm = " + r["engine"],
     }
     out.emit(line)
+
+
+# ------------------------------------------------------------------------------------------------ GPU helpers
+def _flat(res):
+    return np.concatenate([[res.loglike, res.log_mu_sel, res.log_mu2, res.neff_sel], res.dloglike, res.dlog_mu_sel])
+
+
+def time_config(name, wa, world, local_rank, dist, steps=100, warm=5):
+    """One of the other BASELINE.json shapes, sharded like the headline: device-timed back-to-back evaluations and
+    the end-to-end host call."""
+    import torch
+
+    from bumpcosmology_b200.catalogs import THETA_DEFAULT, make_catalog
+    from bumpcosmology_b200.likelihood import Hyperlikelihood, ShardedHyperlikelihood
+    cat = name if not isinstance(name, str) else make_catalog(name)
+    theta = np.concatenate([THETA_DEFAULT, [0.3]]) if wa else THETA_DEFAULT
+    if world > 1:
+        like = ShardedHyperlikelihood(cat.as_args(), device=local_rank, wa=wa)
+        local = like.local
+    else:
+        like = local = Hyperlikelihood(*cat.as_args(), device=local_rank, wa=wa)
+    like(theta)
+    local.time_evals(theta, warm)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, _ = local.time_evals(theta, steps)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = like(theta)
+    e2e = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = float(t.item())
+    _, ker = local.time_evals(theta, 10, kernel=True)
+    rec = {"workload": f"{cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections" + (", w0-wa" if wa else ""),
+           "evals_per_s": steps / (ms * 1e-3), "us_per_eval": 1e3 * ms / steps, "e2e_evals_per_s": steps / e2e,
+           "stream_kernel_us": 1e3 * ker / 10, "steps": steps, "logl": res.logl}
+    like.close() if hasattr(like, "close") else local.close()
+    return rec
+
+
+def nuts_record(workload, warmup, samples, chains, device, cpu_s_per_eval=None):
+    """NUTS(dense_mass=True), `chains` x (warmup + samples), seed 1652819403 (run_cosmo_fit.py:17-19,45-49) with the
+    library's C++ driver, one context and host thread per chain."""
+    from bumpcosmology_b200 import intensity_models as im, nuts
+    from bumpcosmology_b200.catalogs import make_catalog
+    cat = make_catalog(workload)
+    models = [im.pop_cosmo_model(*cat.as_args(), device=device) for _ in range(chains)]
+    t0 = time.perf_counter()
+    r = nuts.run_mcmc(models, warmup, samples, chains, seed=1652819403, native=True)
+    wall = time.perf_counter() - t0
+    ess = r["ess_bulk"][:14]
+    rec = {"workload": f"{workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections",
+           "chains": chains, "warmup": warmup, "samples": samples, "dense_mass": True, "seed": 1652819403,
+           "driver": "c++ (bump_nuts_chain), chains in parallel host threads on one GPU",
+           "wall_s": wall, "sampling_s": r["sampling_s"], "min_bulk_ess": float(ess.min()),
+           "ess_per_s_total": float(ess.min() / wall), "ess_per_s_sampling": float(ess.min() / r["sampling_s"]),
+           "rhat_max": float(r["rhat"][:14].max()),
+           "divergences": int(sum(c["stats"]["diverging"].sum() for c in r["chains"])),
+           "mean_tree_depth": float(np.mean([c["stats"]["depth"].mean() for c in r["chains"]])),
+           "step_size": [float(c["step_size"]) for c in r["chains"]],
+           "model_evals": int(r["n_leapfrog_total"]), "evals_per_s": r["n_leapfrog_total"] / wall}
+    if cpu_s_per_eval:
+        # the CPU arm of the sampler: the same driver, the same number of model evaluations, each costing one
+        # evaluation of the CPU port (measured in this run at this shape); chains in sequence on all cores
+        cpu_wall = r["n_leapfrog_total"] * cpu_s_per_eval
+        rec["cpu_arm"] = {"kind": "derived", "s_per_eval": cpu_s_per_eval, "wall_s": cpu_wall,
+                          "ess_per_s_total": float(ess.min() / cpu_wall),
+                          "note": "same sampler and evaluation count driving the C++/OpenMP port: model evaluations "
+                                  "x measured CPU seconds per evaluation at this shape (all host cores)"}
+    for m in models:
+        m.close()
+    return rec
 
 
 def main():
@@ -235,6 +319,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("BUMP_BENCH_WORKLOAD", "o5"))
     ap.add_argument("--exchange", default=os.environ.get("BUMP_EXCHANGE", "p2p"), choices=("torch", "nccl", "p2p"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the GWTC-3 / O4 / w0-wa sub-records")
+    ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS sub-record (1 GPU only)")
     ap.add_argument("--wa", action="store_true",
                     help="w0-wa (CPL) dark energy variant (BASELINE.json config 5): 15 parameters, the d_L(z) grid is "
                          "rebuilt on the device every step by the cumulative-trapezoid tables kernel")
@@ -252,7 +338,7 @@ def main():
 
     from bumpcosmology_b200 import _lib
     from bumpcosmology_b200.catalogs import THETA_DEFAULT, draw_prior_thetas
-    from bumpcosmology_b200.likelihood import Hyperlikelihood, ShardedHyperlikelihood, shard_catalog
+    from bumpcosmology_b200.likelihood import Hyperlikelihood, ShardedHyperlikelihood
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference)")
@@ -279,6 +365,13 @@ def main():
     n_local = local.nobs * local.nsamp + local.nsel
     K, W = args.steps, args.warmup
 
+    def all_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- device-timed region: K back-to-back evaluations, inputs resident in HBM
     if world == 1:
@@ -295,9 +388,7 @@ def main():
         ms_local, _ = local.time_evals(THETA_DEFAULT, K)
         torch.cuda.synchronize()
         dist.barrier()
-        t = torch.tensor([ms_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total = all_max(ms_local)
     else:
         like(THETA_DEFAULT)
         for _ in range(W):
@@ -311,9 +402,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total = all_max(e0.elapsed_time(e1))
     # ---- end to end through the public host API: host theta in, host result out, every step
     for i in range(W):
         like(thetas[i % len(thetas)])
@@ -324,93 +413,155 @@ def main():
     for i in range(K):
         res = like(thetas[i % len(thetas)])
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    clock_note = None
-    if sampler is not None and len(sampler.lines) < 5:
-        # short timed regions (small catalogs) end before nvidia-smi delivers its first samples: keep the same load
-        # running, untimed, until a handful of samples exist
-        t_end = time.perf_counter() + 2.0
-        while len(sampler.lines) < 5 and time.perf_counter() < t_end:
-            local.time_evals(THETA_DEFAULT, 50) if world == 1 else time.sleep(0.05)
-        clock_note = "timed region shorter than the sampling period: sampled under the same load right after it"
+    e2e_s = all_max(time.perf_counter() - t0)
+    # ---- keep the SAME load running (every rank the same number of evaluations: the exchange is a collective) until
+    # nvidia-smi, which samples every 20 ms, has seen it for about half a second
+    n_extra = int(min(5000, max(20, math.ceil(500.0 / max(ms_total / K, 1e-3)))))
+    if world == 1 or like.exchange in ("nccl", "p2p"):
+        local.time_evals(THETA_DEFAULT, n_extra)
+    else:
+        for _ in range(n_extra):
+            like.launch()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    if clocks is not None and clock_note:
-        clocks["note"] = clock_note
+    if clocks is not None:
+        clocks["note"] = (f"sampled over the timed region and {n_extra} further evaluations of the same load on every "
+                          "rank (the timed region alone is shorter than a few sampling periods)")
     # ---- dominant kernel alone (events around each launch on its stream)
-    _, ker_ms = local.time_evals(THETA_DEFAULT, max(3, min(K, 10)), kernel=True)
-    ker_ms /= max(3, min(K, 10))
+    nk = max(3, min(K, 10))
+    _, ker_ms = local.time_evals(THETA_DEFAULT, nk, kernel=True)
+    ker_ms /= nk
+    ker_ms_max = all_max(ker_ms)
+    # per-kernel timeline of one directly launched evaluation (GPU global timer; every rank launches it: the
+    # peer-memory exchange inside the epilogue is a collective), median of 5
+    tls = [local.timeline(THETA_DEFAULT) for _ in range(5)]
+    timeline = {k: [round(float(np.median([t[k][i] for t in tls])), 2) for i in (0, 1)] for k in tls[0]}
+
+    # ---- N > 1: the sharded result against an unsharded evaluation of the whole catalog on rank 0's GPU
+    result_check = None
+    if world > 1:
+        res_sh = like(THETA_DEFAULT)
+        neff_parts = [None] * world
+        dist.all_gather_object(neff_parts, res_sh.neff)
+        flat_sh = _flat(res_sh)
+        ok = torch.ones(1, device="cuda")
+        if rank == 0:
+            full = Hyperlikelihood(*cat.as_args(), device=local_rank, wa=args.wa)
+            r1 = full(THETA_DEFAULT)
+            full.close()
+            f1 = _flat(r1)
+            gs = max(1.0, float(np.max(np.abs(r1.dloglike))))
+            floor = np.ones_like(f1)
+            floor[4:4 + len(r1.dloglike)] = gs
+            e_hdr = float(np.max(np.abs(flat_sh - f1) / np.maximum(np.abs(f1), floor)))
+            neff_sh = np.concatenate(neff_parts)
+            e_neff = float(np.max(np.abs(neff_sh - r1.neff) / np.maximum(np.abs(r1.neff), 1.0)))
+            result_check = {"max_rel_vs_1gpu": max(e_hdr, e_neff), "header_and_gradients": e_hdr, "neff": e_neff,
+                            "outputs_compared": int(len(f1) + len(neff_sh)), "tolerance": MULTIRANK_TOL,
+                            "logl": res_sh.logl, "logl_1gpu": r1.logl,
+                            "ok": bool(max(e_hdr, e_neff) <= MULTIRANK_TOL)}
+            ok[0] = 1.0 if result_check["ok"] else 0.0
+        dist.broadcast(ok, src=0)
+        multirank_ok = bool(ok.item() > 0.5)
+    else:
+        multirank_ok = True
+        result_check = {"logl": res.logl, "neff_sel": res.neff_sel}
+    plan = local.plan()
+    launches = local.launches_per_eval
+    exchange = getattr(like, "exchange", "none") if world > 1 else "none"
+    ntheta, nobs_local = local.ntheta, local.nobs
+    like.close() if hasattr(like, "close") else local.close()
+
+    # ---- the other BASELINE.json shapes (every rank takes part: they are sharded like the headline)
+    configs = None
+    if not args.no_configs and not args.wa and args.workload == "o5":
+        configs = {}
+        for key, name, wa in (("gwtc3", "gwtc3", False), ("o4", "o4", False), ("o5_wa", cat, True)):
+            try:
+                configs[key] = time_config(name, wa, world, local_rank, dist)
+            except Exception as e:  # noqa: BLE001
+                configs[key] = {"error": str(e)}
+                if dist is not None:
+                    raise
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
+        if not multirank_ok:
+            sys.exit(3)
         return
 
     hbm_peak, peak_src = measured_peaks()
-    algo_bytes = ALGO_BYTES_PER_SAMPLE * n_local
-    achieved = algo_bytes / (ker_ms * 1e-3) / 1e9
     pk = fp64_peak(local_rank)
-    fp64 = None
-    if "dfma_per_s" in pk:
-        inst = EXEC_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
-        algo = ALGO_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
-        fp64 = {"bound": "fp64 pipe", "achieved": inst, "peak": pk["dfma_per_s"], "unit": "fp64 inst/s",
-                "frac": inst / pk["dfma_per_s"], "peak_fp64_tflops": pk["fp64_tflops"],
-                "inst_per_sample_executed": EXEC_FP64_INST_PER_SAMPLE,
-                "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE, "algorithmic_frac": algo / pk["dfma_per_s"],
-                "note": "frac = FP64-pipe instructions the kernel executes (ncu, profiles/) x samples / kernel time, "
-                        "over the DFMA issue rate measured by bump_peak in this run; algorithmic_frac uses SURVEY.md "
-                        "8d's 700 instructions/sample and exceeds 1 because the linear-space kernel needs 3.2x fewer"}
-        # issue ceiling of this instruction mix: 2 cycles per FP64 instruction, +1 for each with three distinct
-        # register operands, +1 per other instruction, per warp-sample and sub-partition (4 per SM)
-        cyc_model = 2 * EXEC_FP64_INST_PER_SAMPLE + EXEC_FP64_3REG_PER_SAMPLE + EXEC_OTHER_INST_PER_SAMPLE
-        sms = pk.get("sms", 148)
-        clk = ((clocks or {}).get("sm_mhz") or pk.get("max_clock_mhz", 1965)) * 1e6   # SM clock sampled under load
-        cyc_meas = ker_ms * 1e-3 * clk * sms * 4 / (n_local / 32)
-        fp64["issue_model"] = {"cycles_per_warp_sample": cyc_model, "measured_cycles_per_warp_sample": cyc_meas,
-                               "frac": cyc_model / cyc_meas,
-                               "fp64_frac_at_model": 2 * EXEC_FP64_INST_PER_SAMPLE / cyc_model,
-                               "note": "what the kernel's own instruction mix allows under the issue rules measured by "
-                                       "tools/micro/fp64_operands.cu (profiles/r01_fp64_issue_microbench.txt); "
-                                       "shared-memory wavefronts run at 82 % of peak beside it"}
+    fp64_rate = pk.get("dfma_per_s") or FP64_PEAK_FALLBACK
+    inst = ALGO_FP64_INST_PER_SAMPLE * n_local / (ker_ms * 1e-3)
+    hbm_achieved = ALGO_BYTES_PER_SAMPLE * n_local / (ker_ms * 1e-3) / 1e9
+    padded = plan["padded_samples"]
     value = K / (ms_total * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cat.nobs} events x {cat.nsamp} samples + {cat.nsel} injections"
-                               + (", w0-wa dark energy (15 parameters)" if args.wa else ""),
-                   "elements": cat.n_elements, "sharding": f"events and injections over {world} rank(s)",
-                   "exchange": getattr(like, "exchange", "none") if world > 1 else "none",
-                   "l2": "per-rank resident columns %.2f GB > 126 MB L2" % (56 * n_local / 1e9)
-                         if 56 * n_local > 2.5e8 else "columns fit in L2 (NUTS re-reads the same data)",
-                   "plan": local.plan(), "catalog_gen_s": round(gen_s, 1), "upload_s": round(upload_s, 2)},
-        "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * local.ntheta,
-                "d2h_bytes_per_step": 8 * (_lib.OUT_HEADER + local.nobs),
+        "dtype": "f64", "data": "synthetic", "config": config_of(args, cat),
+        "run": {"sharding": f"whole events and a contiguous injection range per rank, {world} rank(s)",
+                "exchange": exchange, "plan": plan, "catalog_gen_s": round(gen_s, 1), "upload_s": round(upload_s, 2),
+                "stream_kernel_ms_max_over_ranks": ker_ms_max,
+                "timeline_us": timeline,
+                "timeline_note": "[first block start, last block end] of each kernel of one directly launched "
+                                 "evaluation on rank 0, microseconds from the first kernel's start"},
+        "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * ntheta,
+                "d2h_bytes_per_step": 8 * (_lib.OUT_HEADER + nobs_local),
                 "note": "public host call Hyperlikelihood.__call__(theta): theta from host memory, result to "
                         "host memory, wall clock; the catalog is uploaded once (upload_s), as the reference's "
                         "jitted model closes over its data"},
-        "gpu_launches": K * local.launches_per_eval,
+        "gpu_launches": K * launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_SAMPLE * n_local,
-                     "traffic_note": "dram__bytes_read+write of one launch from ncu --set full (profiles/), per sample "
-                                     "x this rank's samples: 7 resident fp64 columns incl. hoisted logs",
-                     "kernel": "stream_kernel",
-                     "kernel_ms": ker_ms, "peak_source": peak_src,
-                     "note": "algorithmic 32 B/sample; the fp64 path is FP64-pipe bound, see fp64_pipe"},
-        "fp64_pipe": fp64,
-        "result_check": {"logl": res.logl, "neff_sel": res.neff_sel},
+        "roofline": {"bound": "fp64 pipe", "achieved": inst, "peak": fp64_rate, "unit": "FP64 warp-lane inst/s",
+                     "frac": inst / fp64_rate,
+                     "traffic": 8 * 7 * padded,
+                     "kernel": "stream_kernel", "kernel_ms": ker_ms,
+                     "peak_source": "DFMA issue rate measured in this run by bumpcosmology_b200/bump_peak "
+                                    f"({pk.get('fp64_tflops', 'n/a')} TFLOP/s)" if "dfma_per_s" in pk else
+                                    "fallback: DFMA rate measured on this pool's B200s in round 1 (bump_peak failed)",
+                     "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE,
+                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                             "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "peak_source": peak_src},
+                     "note": "the path is transcendental-bound (8 exp + 4 reciprocals per sample, no contraction): the "
+                             "binding roofline is the FP64 pipe, as BASELINE.json's north star allows; achieved = "
+                             "217.5 FP64-pipe instructions per sample (frozen algorithmic count, DESIGN.md section 4) x "
+                             "this rank's samples / the kernel's launch time; traffic = the 7 resident fp64 columns "
+                             "of the padded samples, which the kernel reads exactly once (ncu: profiles/)"},
+        "result_check": result_check,
     }
+    if configs is not None:
+        line["configs"] = configs
+    cpu_gwtc3 = None
     if world == 1 and not args.no_cpu_baseline and not args.wa:
-        line["cpu_baseline"] = cpu_baseline(cat)
+        cb = cpu_arm(cat, 6, 1)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+                                "sample": cb["sample"], "s_per_eval_median": cb["s_per_eval_median"],
+                                "host_cpus": cb["host_cpus"], "engine": cb["engine"]}
+        if not args.no_nuts:
+            from bumpcosmology_b200.catalogs import make_catalog
+            g = time_cpu_port(make_catalog("gwtc3"), 20, 3)
+            cpu_gwtc3 = g["s_per_eval_median"] if g else None
+    if world == 1 and not args.no_nuts and not args.wa and args.workload == "o5":
+        try:
+            line["nuts"] = {
+                "gwtc3_nuts": nuts_record("gwtc3_nuts", 1000, 1000, 4, local_rank, cpu_gwtc3),
+                # the standard catalog keeps ~3 % of its samples at the model's hard cut m >= 5 (intensity_models.py:
+                # 149): logL jumps as (h, Om, w) move samples across it and NUTS stalls, so
+                # this run is bounded to 4 x (150 + 150) and reported as found
+                "gwtc3": nuts_record("gwtc3", 150, 150, 4, local_rank, cpu_gwtc3),
+                "metric": "min bulk-ESS over the 14 likelihood sites / wall seconds (warm-up included) and / "
+                          "sampling seconds; rank-normalised split-chain ESS (arviz formula)"}
+        except Exception as e:  # noqa: BLE001
+            line["nuts"] = {"error": str(e)}
     out.emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if not multirank_ok:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

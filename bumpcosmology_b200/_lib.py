@@ -13,7 +13,8 @@ NTHETA = 14
 NTHETA_MAX = 15
 OUT_LOGLIKE, OUT_LOG_MU_SEL, OUT_LOG_MU2, OUT_NEFF_SEL = 0, 1, 2, 3
 OUT_DLOGLIKE, OUT_DLOG_MU = 4, 19
-OUT_NVALID_EVT, OUT_NVALID_SEL, OUT_NOBS, OUT_NSEL = 34, 35, 36, 37
+OUT_NVALID_EVT, OUT_NVALID_SEL, OUT_NOBS, OUT_NSEL, OUT_STATUS = 34, 35, 36, 37, 38
+E_INVALID, E_CUDA, E_NOGPU, E_NCCL, E_EXCHANGE = 1, 2, 3, 4, 5
 OUT_HEADER = 40
 PARTIAL_LEN = 128
 FLAG_WA, FLAG_NO_GRAPH, FLAG_NO_SORT, FLAG_FIXED_COSMO = 1, 2, 4, 8
@@ -42,6 +43,8 @@ SIGNATURES = {
     "bump_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bump_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "bump_p2p_detach": (C.c_int, [C.c_void_p]),
+    "bump_p2p_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
+    "bump_debug_timeline": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64]),
     "bump_debug_tables": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64]),
     "bump_time_evals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bump_launches_per_eval": (C.c_int, [C.c_void_p]),

@@ -106,7 +106,15 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
 // the epoch, waits until its own mailbox holds the current epoch from every rank, and finalizes — no NCCL call, no
 // extra launch.  Two parities: a rank can run at most one evaluation ahead of the slowest peer (it needs that peer's
 // current partial to finish), so the buffer it overwrites is never still being read.
+//
+// Failure is COLLECTIVE and STICKY.  A rank that waits longer than `timeout_ns` for a peer gives up, does NOT advance
+// its epoch, marks its exchange state broken and overwrites its flag in every peer's mailbox (both parities) with
+// P2P_POISON; a peer that is waiting for it - or arrives later, however late - finds the poison instead of the epoch,
+// fails the same way and poisons everybody else in turn.  Every evaluation after that fails immediately until the
+// ranks detach and attach again.  The result header carries the status word (OUT_STATUS) next to NaN outputs, and
+// bump_eval returns BUMP_E_EXCHANGE: ranks can no longer disagree about whether an evaluation happened.
 constexpr int P2P_MAX_RANKS = 16;
+constexpr unsigned long long P2P_POISON = ~0ull;
 struct Mailbox {
     double mail[2][P2P_MAX_RANKS][PARTIAL_LEN];
     unsigned long long flag[2][P2P_MAX_RANKS];
@@ -114,39 +122,64 @@ struct Mailbox {
 struct Peers {
     Mailbox* box[P2P_MAX_RANKS];   // box[r] = rank r's mailbox as mapped into this process (box[rank] = local)
     int nranks, rank;
+    unsigned long long timeout_ns;
 };
+// exchange state of a context: [0] epoch of the last completed exchange, [1] broken (sticky)
 
-// Called by all threads of ONE block.  Returns false on timeout (a peer never arrived).
-__device__ inline bool p2p_exchange(const Peers& peers, const double* __restrict__ partial,
-                                    unsigned long long* __restrict__ epoch_counter) {
-    __shared__ int s_ok;
+// Called by all threads of ONE block.  Returns STATUS_OK, STATUS_EXCHANGE_TIMEOUT (a peer never arrived) or
+// STATUS_EXCHANGE_POISONED (a peer failed, now or earlier).
+__device__ inline double p2p_exchange(const Peers& peers, const double* __restrict__ partial,
+                                      unsigned long long* __restrict__ state) {
+    __shared__ int s_status;
     const int tid = threadIdx.x;
-    const unsigned long long epoch = *epoch_counter + 1ull;
+    const unsigned long long epoch = state[0] + 1ull;
+    const bool broken = state[1] != 0ull;
     const int par = (int)(epoch & 1ull);
-    if (tid == 0) s_ok = 1;
-    for (int r = 0; r < peers.nranks; ++r)
-        for (int k = tid; k < PARTIAL_LEN; k += blockDim.x) peers.box[r]->mail[par][peers.rank][k] = partial[k];
+    if (tid == 0) s_status = broken ? 2 : 0;
+    if (!broken)
+        for (int r = 0; r < peers.nranks; ++r)
+            for (int k = tid; k < PARTIAL_LEN; k += blockDim.x) peers.box[r]->mail[par][peers.rank][k] = partial[k];
     __threadfence_system();
     __syncthreads();
-    if (tid < peers.nranks) {
+    if (tid < peers.nranks && !broken) {
         *reinterpret_cast<volatile unsigned long long*>(&peers.box[tid]->flag[par][peers.rank]) = epoch;
         const volatile unsigned long long* mine = &peers.box[peers.rank]->flag[par][tid];
-        const long long t0 = clock64();
-        while (*mine != epoch) {
-            if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer is gone; fail instead of hanging the GPU
-                s_ok = 0;
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+            const unsigned long long v = *mine;
+            if (v == epoch) break;
+            if (v == P2P_POISON) {
+                atomicMax(&s_status, 2);
+                break;
+            }
+            if (global_ns() - t0 > peers.timeout_ns) {   // a peer is gone: fail instead of hanging the GPU
+                atomicMax(&s_status, 1);
                 break;
             }
         }
     }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) *epoch_counter = epoch;
-    return s_ok != 0;
+    const int st = s_status;
+    if (st != 0) {
+        if (tid < peers.nranks && tid != peers.rank) {   // tell every peer, whichever evaluation it is in
+            *reinterpret_cast<volatile unsigned long long*>(&peers.box[tid]->flag[0][peers.rank]) = P2P_POISON;
+            *reinterpret_cast<volatile unsigned long long*>(&peers.box[tid]->flag[1][peers.rank]) = P2P_POISON;
+        }
+        if (tid == 0) state[1] = 1ull;
+        __threadfence_system();
+    } else if (tid == 0) {
+        state[0] = epoch;
+    }
+    __syncthreads();
+    return st == 0 ? STATUS_OK : st == 1 ? STATUS_EXCHANGE_TIMEOUT : STATUS_EXCHANGE_POISONED;
 }
 
-__global__ void finalize_kernel(const double* __restrict__ partials, const int nranks, double* __restrict__ out) {
+__global__ void finalize_kernel(const double* __restrict__ partials, const int nranks, double* __restrict__ out,
+                                unsigned long long* __restrict__ tl) {
+    timeline_begin(tl, TL_FINALIZE);
     if (threadIdx.x == 0 && blockIdx.x == 0) finalize_merge(partials, nranks, out);
+    timeline_end(tl, TL_FINALIZE);
 }
 
 // Merge two max-shifted accumulators (m, a[NACC]) <- (m, a) (+) (m2, b[NACC]).
@@ -203,11 +236,12 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
                 const int lpe /* lanes per event: power of two <= 32 */, const double* __restrict__ blob,
                 double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
                 double* __restrict__ partial, double* __restrict__ out_header, const Peers* __restrict__ peers,
-                unsigned long long* __restrict__ epoch_counter) {
+                unsigned long long* __restrict__ exchange_state, unsigned long long* __restrict__ tl) {
     __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
     __shared__ double s_max;
     __shared__ bool is_last;
     const int tid = threadIdx.x;
+    timeline_begin(tl, TL_EPILOGUE);
     const int nobs = wk.nobs;
     const int epb = EPI_THREADS / lpe;   // events per block
     const int nb_evt = (nobs + epb - 1) / epb;
@@ -314,7 +348,10 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) {
+        timeline_end(tl, TL_EPILOGUE);
+        return;
+    }
     __threadfence();
     if (tid < NFEAT + 3) {
         double s = 0.0;
@@ -343,17 +380,21 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         __threadfence();
         __syncthreads();
         if (peers) {   // multi-rank, fused exchange over peer memory
-            const bool ok = p2p_exchange(*peers, partial, epoch_counter);
+            const double status = p2p_exchange(*peers, partial, exchange_state);
             if (tid == 0) {
-                const int par = (int)(*epoch_counter & 1ull);
-                finalize_merge(&peers->box[peers->rank]->mail[par][0][0], peers->nranks, out_header);
-                if (!ok)
-                    for (int k = 0; k < OUT_NVALID_EVT; ++k) out_header[k] = NAN;
+                if (status == STATUS_OK) {
+                    const int par = (int)(exchange_state[0] & 1ull);
+                    finalize_merge(&peers->box[peers->rank]->mail[par][0][0], peers->nranks, out_header);
+                } else {   // the exchange failed on every rank (see p2p_exchange): no result, and say so
+                    for (int k = 0; k < OUT_HEADER; ++k) out_header[k] = (k < OUT_NVALID_EVT) ? NAN : 0.0;
+                    out_header[OUT_STATUS] = status;
+                }
             }
         } else if (tid == 0) {
             finalize_merge(partial, 1, out_header);
         }
     }
+    timeline_end(tl, TL_EPILOGUE);
 }
 
 }  // namespace bump

@@ -161,6 +161,25 @@ enum PartialIdx {
 // output header (must match include/bump.h)
 constexpr int OUT_LOGLIKE = 0, OUT_LOG_MU_SEL = 1, OUT_LOG_MU2 = 2, OUT_NEFF_SEL = 3, OUT_DLOGLIKE = 4,
               OUT_DLOG_MU = 19, OUT_NVALID_EVT = 34, OUT_NVALID_SEL = 35, OUT_NOBS = 36, OUT_NSEL = 37,
-              OUT_HEADER = 40;
+              OUT_STATUS = 38, OUT_HEADER = 40;
+// OUT_STATUS values (0 = ok): the peer-memory exchange of a multi-rank evaluation failed
+constexpr double STATUS_OK = 0.0, STATUS_EXCHANGE_TIMEOUT = 1.0, STATUS_EXCHANGE_POISONED = 2.0;
+
+// ---- optional per-kernel timeline (bump_debug_timeline): first block start / last block end of every kernel of one
+// evaluation on the GPU's global nanosecond timer.  tl == nullptr (always, on the normal path) costs one predicate.
+enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE, TL_N };
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void timeline_begin(unsigned long long* tl, const int k) {
+    if (tl != nullptr && threadIdx.x == 0) atomicMin(tl + 2 * k, global_ns());
+}
+__device__ __forceinline__ void timeline_end(unsigned long long* tl, const int k) {
+    if (tl != nullptr && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, global_ns());
+}
+#endif
 
 }  // namespace bump

@@ -1,11 +1,13 @@
 // libbump_b200.so — C ABI (include/bump.h) over the sm_100a kernels.  CUDA runtime only; no torch, no CPU fallback.
 //
-// One evaluation = 4 launches replayed from a CUDA graph:
-//   tables_kernel    (bump_tables.cuh)   theta -> PISN and cosmology tables + tangents  (F1-F2 of SURVEY.md 2.2)
-//   records_kernel   (bump_tables.cuh)   packed per-bin records, d_L bucket table, scalars (F3)
+// One evaluation = 3 kernel launches (+ one 512-byte device-to-device copy) replayed from a CUDA graph:
+//   prologue_kernel  (bump_tables.cuh)   theta -> PISN and cosmology tables + tangents (F1-F2 of SURVEY.md 2.2), then
+//                                        in its last block the packed per-bin records, d_L bucket table, scalars (F3)
+//   (copy node)                          the scalars -> this context's constant-bank slot
 //   stream_kernel    (bump_stream.cuh)   one pass over the SoA columns -> per-warp records (F4-F7 + reverse pass)
-//   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial, and (single rank) the result
-//   [multi-rank: ncclAllGather of the 1 KiB partial, then finalize_kernel: rank-ordered merge -> result header]
+//   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial, and (single rank, or peer-memory
+//                                        exchange) the result
+//   [NCCL exchange: ncclAllGather of the 1 KiB partial, then finalize_kernel: rank-ordered merge -> result header]
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
@@ -202,8 +204,13 @@ struct bump_ctx {
     // fused exchange over peer memory
     Mailbox* d_mailbox = nullptr;            // this rank's mailbox (cudaMalloc: IPC-exportable)
     Peers* d_peers = nullptr;                // device copy of the peer table (null: not attached)
-    unsigned long long* d_epoch = nullptr;
+    Peers h_peers{};
+    unsigned long long* d_epoch = nullptr;   // exchange state: [0] epoch, [1] broken
+    double p2p_timeout_s = 10.0;
     void* peer_ptr[P2P_MAX_RANKS] = {};      // mappings opened with cudaIpcOpenMemHandle
+    bool slot_counted = false;
+    bool slot_pinned = false;                // an evaluation of this context was captured into a caller's graph
+    unsigned long long* d_timeline = nullptr;   // bump_debug_timeline
 };
 
 namespace {
@@ -336,7 +343,7 @@ EvalConsts consts_of(const bump_ctx* c) {
 }
 
 // stream_kernel<WA, FIXED, SLOT> of a context (its mode and its constant-bank slot)
-using StreamKernel = void (*)(const Columns, const Work, const int*, const double*, double*);
+using StreamKernel = void (*)(const Columns, const Work, const int*, const double*, double*, unsigned long long*);
 template <int SLOT>
 StreamKernel stream_kernel_of(const bool fixed, const bool wa) {
     return fixed ? stream_kernel<false, true, SLOT> : wa ? stream_kernel<true, false, SLOT> : stream_kernel<false, false, SLOT>;
@@ -352,72 +359,96 @@ StreamKernel stream_kernel_at(const bool fixed, const bool wa, const int slot) {
 static_assert(NSLOT == 4, "stream_kernel_at enumerates the slots");
 StreamKernel stream_kernel_for(const bump_ctx* c) { return stream_kernel_at(c->fixed, c->use_wa, c->slot); }
 
-// The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
+// The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches and one 512-byte copy.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
-                   cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr) {
-    tables_kernel<<<NM + COS_CHUNKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_ticket + 2, c->use_wa ? 1 : 0,
-                                                          c->d_aux + AUX_DOUBLES, c->d_ticket + 4);
-    records_kernel<<<REC_BLOCKS + 1, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 2, consts_of(c),
-                                                          c->d_ticket + 4);
+                   cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr,
+                   unsigned long long* tl = nullptr) {
+    prologue_kernel<<<PRO_BLOCKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 4, consts_of(c), tl);
     CK(cudaMemcpyToSymbolAsync(K_SC4, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL,
                                sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0)
-        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, stream_smem_bytes(c->use_wa, c->fixed), s>>>(columns_of(c), c->work, c->d_rec_off,
-                                                                                  c->d_blob, c->d_part);
+        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, stream_smem_bytes(c->use_wa, c->fixed), s>>>(
+            columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part, tl);
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
     epilogue_kernel<<<nb_evt + 1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->lpe,
                                                        c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
-                                                       fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch);
+                                                       fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl);
     CK(cudaGetLastError());
     return BUMP_OK;
 }
 
 int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStream_t s, cudaEvent_t k0 = nullptr,
-                cudaEvent_t k1 = nullptr) {
-    // single rank, or peer-memory exchange: the epilogue's last block finalizes in place (4 launches per evaluation)
-    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev))
+                cudaEvent_t k1 = nullptr, unsigned long long* tl = nullptr) {
+    // single rank, or peer-memory exchange: the epilogue's last block finalizes in place (3 launches per evaluation)
+    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev, tl))
         return r;
     if (c->comm) {
         NCK(g_nccl.AllGather(c->d_partial, c->d_gather, PARTIAL_LEN, NCCL_FLOAT64, c->comm, s));
-        finalize_kernel<<<1, 32, 0, s>>>(c->d_gather, c->nranks, out_dev);
+        finalize_kernel<<<1, 32, 0, s>>>(c->d_gather, c->nranks, out_dev, tl);
         CK(cudaGetLastError());
     }
     return BUMP_OK;
 }
 
-// A constant-bank slot (K_SC4[slot]) is shared by the contexts of a device that were assigned to it: their
+// A constant-bank slot (K_SC4[slot]) may be shared by several contexts of a device (more than NSLOT contexts): their
 // evaluations are chained through an event so that two of them never have an evaluation in flight at the same time.
-// Contexts on different slots run concurrently.
+// Contexts on different slots run concurrently.  An evaluation that is being CAPTURED into a caller's CUDA graph
+// (bump_eval_device on a capturing stream: how an XLA command buffer or torch.cuda.graph calls it) cannot take part
+// in that chain - the graph replays later, outside the library's control, and events recorded inside a capture
+// cannot be waited on outside it - so capture requires a context that owns its slot alone, and pins the slot: no
+// later context is assigned to it.
 std::mutex g_dev_mutex;                  // slot assignment
 std::mutex g_slot_mutex[64 * NSLOT];     // launch order within a slot
 cudaEvent_t g_dev_event[64 * NSLOT] = {};
-int g_dev_next_slot[64] = {};
+int g_slot_users[64 * NSLOT] = {};
+bool g_slot_pinned[64 * NSLOT] = {};
 
-struct DeviceChain {
+struct SlotGuard {
     std::unique_lock<std::mutex> lock;
     cudaEvent_t ev = nullptr;
-    cudaStream_t s;
-    DeviceChain(const bump_ctx* c, cudaStream_t stream) : s(stream) {
-        if (c->device < 0 || c->device >= 64) return;
+    cudaStream_t s = nullptr;
+    int begin(bump_ctx* c, cudaStream_t stream) {
+        s = stream;
+        if (c->device < 0 || c->device >= 64) return BUMP_OK;
         const int k = c->device * NSLOT + c->slot;
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        CK(cudaStreamIsCapturing(stream, &st));
+        if (st != cudaStreamCaptureStatusNone) {
+            std::lock_guard<std::mutex> lk(g_dev_mutex);
+            if (g_slot_users[k] > 1)
+                return fail(BUMP_E_INVALID, "stream capture needs a context that owns its constant-bank slot: at most "
+                                            "4 contexts per device may be alive when one of them is captured");
+            g_slot_pinned[k] = true;
+            c->slot_pinned = true;
+            return BUMP_OK;   // ordering inside the caller's graph is the caller's stream order
+        }
         lock = std::unique_lock<std::mutex>(g_slot_mutex[k]);
-        if (!g_dev_event[k]) cudaEventCreateWithFlags(&g_dev_event[k], cudaEventDisableTiming);
+        if (!g_dev_event[k]) CK(cudaEventCreateWithFlags(&g_dev_event[k], cudaEventDisableTiming));
         ev = g_dev_event[k];
-        cudaStreamWaitEvent(s, ev, 0);
+        CK(cudaStreamWaitEvent(s, ev, 0));
+        return BUMP_OK;
     }
-    ~DeviceChain() {
+    ~SlotGuard() {
         if (ev) cudaEventRecord(ev, s);
     }
 };
 
-int ensure_ready(bump_ctx* c) {
+int ensure_ready(bump_ctx* c, cudaStream_t capture_check = nullptr) {
     if (!c) return fail(BUMP_E_INVALID, "null context");
     if (int r = set_device(c)) return r;
-    if (c->plan_dirty)
+    if (c->plan_dirty) {
+        if (capture_check) {   // building the plan allocates: not allowed while the caller's stream is capturing
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            CK(cudaStreamIsCapturing(capture_check, &st));
+            if (st != cudaStreamCaptureStatusNone)
+                return fail(BUMP_E_INVALID, "call bump_plan_info (or one evaluation) after the uploads and before "
+                                            "capturing bump_eval_device into a graph");
+        }
         if (int r = build_plan(c)) return r;
+    }
     return BUMP_OK;
 }
 
@@ -440,7 +471,8 @@ int ensure_graph(bump_ctx* c) {
 int run_once(bump_ctx* c) {   // d_theta -> d_out on the context stream
     if (!(c->flags & BUMP_FLAG_NO_GRAPH))
         if (int r = ensure_graph(c)) return r;
-    DeviceChain chain(c, c->stream);
+    SlotGuard chain;
+    if (int r = chain.begin(c, c->stream)) return r;
     if (c->flags & BUMP_FLAG_NO_GRAPH) return launch_eval(c, c->d_theta, c->d_out, c->stream);
     CK(cudaGraphLaunch(c->graph, c->stream));
     return BUMP_OK;
@@ -485,7 +517,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaMemset(c->d_theta, 0, sizeof(double) * NTHETA_MAX));
-    CK(cudaMalloc(&c->d_aux, sizeof(double) * (AUX_DOUBLES + AUX_CHAIN_DOUBLES)));
+    CK(cudaMalloc(&c->d_aux, sizeof(double) * AUX_DOUBLES));
     CK(cudaMalloc(&c->d_blob, BLOB_BYTES_MAX));
     CK(cudaMemset(c->d_blob, 0, BLOB_BYTES_MAX));
     {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
@@ -494,16 +526,28 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * NEXPT, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
-    // [0] unused, [1] epilogue ticket, [2] bad-theta flag, [3] bad-input flag, [4..7] cosmology scan-chain flags
+    // [0] unused, [1] epilogue ticket, [2] unused, [3] bad-input flag, [4] prologue ticket, [5] bad-theta flag
     CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8));
     CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 8));
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_fixed_tab, sizeof(double) * NZ));
-    if (device < 64) {   // round-robin over the constant-bank slots of this device
+    if (device < 64) {   // the least-used constant-bank slot of this device that no captured graph has pinned
         std::lock_guard<std::mutex> lk(g_dev_mutex);
-        c->slot = g_dev_next_slot[device]++ % NSLOT;
+        int best = -1;
+        for (int k = 0; k < NSLOT; ++k)
+            if (!g_slot_pinned[device * NSLOT + k] &&
+                (best < 0 || g_slot_users[device * NSLOT + k] < g_slot_users[device * NSLOT + best]))
+                best = k;
+        if (best < 0) {
+            bump_ctx_destroy(c);
+            return fail(BUMP_E_INVALID, "every constant-bank slot of this device is pinned by a context whose "
+                                        "evaluation was captured into a graph: destroy one of them first");
+        }
+        c->slot = best;
+        ++g_slot_users[device * NSLOT + best];
+        c->slot_counted = true;
     }
     CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize,
                             stream_smem_bytes(c->use_wa, c->fixed)));
@@ -512,8 +556,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         // have to drain and re-partition L1 / shared memory between the four launches (GWTC-3 shape: 56.8 -> 55.3 us per evaluation)
         const int co = cudaSharedmemCarveoutMaxShared;
         CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-        CK(cudaFuncSetAttribute(records_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
+        CK(cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
         CK(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
         CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co));
     }
@@ -524,7 +567,13 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
 void bump_ctx_destroy(bump_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->slot_counted) {
+        std::lock_guard<std::mutex> lk(g_dev_mutex);
+        --g_slot_users[c->device * NSLOT + c->slot];
+        if (c->slot_pinned) g_slot_pinned[c->device * NSLOT + c->slot] = false;
+    }
+    cudaFree(c->d_timeline);
     free_plan(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
@@ -584,29 +633,39 @@ int bump_eval(bump_ctx* c, const double* theta, double* out) {
     CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * c->out_len, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     memcpy(out, c->h_out, sizeof(double) * c->out_len);
+    if (c->h_out[OUT_STATUS] != STATUS_OK)
+        return fail(BUMP_E_EXCHANGE,
+                    c->h_out[OUT_STATUS] == STATUS_EXCHANGE_TIMEOUT
+                        ? "multi-rank exchange timed out: a peer did not deliver its partial (this evaluation failed on "
+                          "every rank; detach and re-attach the peer mailboxes to continue)"
+                        : "multi-rank exchange failed on a peer rank (poisoned mailbox; this evaluation failed on every "
+                          "rank; detach and re-attach the peer mailboxes to continue)");
     return BUMP_OK;
 }
 
 int bump_eval_device(bump_ctx* c, const double* theta_dev, double* out_dev, void* stream) {
     if (!theta_dev || !out_dev) return fail(BUMP_E_INVALID, "null theta/out");
-    if (int r = ensure_ready(c)) return r;
-    DeviceChain chain(c, static_cast<cudaStream_t>(stream));
-    return launch_eval(c, theta_dev, out_dev, static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int r = ensure_ready(c, s)) return r;
+    SlotGuard chain;
+    if (int r = chain.begin(c, s)) return r;
+    return launch_eval(c, theta_dev, out_dev, s);
 }
 
 int bump_eval_partial_device(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev,
                              void* stream) {
     if (!theta_dev || !partial_dev) return fail(BUMP_E_INVALID, "null theta/partial");
-    if (int r = ensure_ready(c)) return r;
-    DeviceChain chain(c, static_cast<cudaStream_t>(stream));
-    return launch_partial(c, theta_dev, partial_dev, neff_dev ? neff_dev : c->d_out + OUT_HEADER,
-                          static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int r = ensure_ready(c, s)) return r;
+    SlotGuard chain;
+    if (int r = chain.begin(c, s)) return r;
+    return launch_partial(c, theta_dev, partial_dev, neff_dev ? neff_dev : c->d_out + OUT_HEADER, s);
 }
 
 int bump_finalize_device(bump_ctx* c, const double* partials_dev, int nranks, double* out_header_dev, void* stream) {
     if (!c || !partials_dev || !out_header_dev || nranks < 1) return fail(BUMP_E_INVALID, "bad finalize arguments");
     if (int r = set_device(c)) return r;
-    finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials_dev, nranks, out_header_dev);
+    finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials_dev, nranks, out_header_dev, nullptr);
     CK(cudaGetLastError());
     return BUMP_OK;
 }
@@ -618,7 +677,8 @@ int bump_eval_partial(bump_ctx* c, const double* theta, double* partial, double*
     memcpy(c->h_theta, theta, sizeof(double) * nth);
     CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
     {
-        DeviceChain chain(c, c->stream);
+        SlotGuard chain;
+        if (int r = chain.begin(c, c->stream)) return r;
         if (int r = launch_partial(c, c->d_theta, c->d_partial, c->d_out + OUT_HEADER, c->stream)) return r;
     }
     CK(cudaMemcpyAsync(partial, c->d_partial, sizeof(double) * PARTIAL_LEN, cudaMemcpyDeviceToHost, c->stream));
@@ -664,8 +724,8 @@ int bump_p2p_export(bump_ctx* c, void* handle64) {
     if (!c->d_mailbox) {
         CK(cudaMalloc(&c->d_mailbox, sizeof(Mailbox)));
         CK(cudaMemset(c->d_mailbox, 0, sizeof(Mailbox)));
-        CK(cudaMalloc(&c->d_epoch, sizeof(unsigned long long)));
-        CK(cudaMemset(c->d_epoch, 0, sizeof(unsigned long long)));
+        CK(cudaMalloc(&c->d_epoch, 2 * sizeof(unsigned long long)));
+        CK(cudaMemset(c->d_epoch, 0, 2 * sizeof(unsigned long long)));
         CK(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -684,6 +744,8 @@ int bump_p2p_attach(bump_ctx* c, const void* handles, int nranks, int rank) {
     memset(&p, 0, sizeof(p));
     p.nranks = nranks;
     p.rank = rank;
+    if (const char* e = getenv("BUMP_P2P_TIMEOUT_S")) c->p2p_timeout_s = std::max(1e-3, atof(e));
+    p.timeout_ns = (unsigned long long)(c->p2p_timeout_s * 1e9);
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) {
             p.box[r] = c->d_mailbox;
@@ -698,6 +760,7 @@ int bump_p2p_attach(bump_ctx* c, const void* handles, int nranks, int rank) {
     }
     if (!c->d_peers) CK(cudaMalloc(&c->d_peers, sizeof(Peers)));
     CK(cudaMemcpy(c->d_peers, &p, sizeof(p), cudaMemcpyHostToDevice));
+    c->h_peers = p;
     c->nranks = nranks;
     c->rank = rank;
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
@@ -711,9 +774,26 @@ int bump_p2p_detach(bump_ctx* c) {
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
         if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]), c->peer_ptr[r] = nullptr;
     cudaFree(c->d_peers), c->d_peers = nullptr;
+    // a fresh mailbox and exchange state (epoch 0, not broken): after a failed exchange every rank detaches, the ranks
+    // synchronise on the host, and then export / attach again
+    if (c->d_mailbox) CK(cudaMemset(c->d_mailbox, 0, sizeof(Mailbox)));
+    if (c->d_epoch) CK(cudaMemset(c->d_epoch, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaDeviceSynchronize());
     c->nranks = 1;
     c->rank = 0;
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    return BUMP_OK;
+}
+
+int bump_p2p_set_timeout(bump_ctx* c, double seconds) {
+    if (!c || !(seconds > 0.0)) return fail(BUMP_E_INVALID, "bad timeout");
+    if (int r = set_device(c)) return r;
+    c->p2p_timeout_s = seconds;
+    if (c->d_peers) {
+        CK(cudaStreamSynchronize(c->stream));
+        c->h_peers.timeout_ns = (unsigned long long)(seconds * 1e9);
+        CK(cudaMemcpy(c->d_peers, &c->h_peers, sizeof(Peers), cudaMemcpyHostToDevice));
+    }
     return BUMP_OK;
 }
 
@@ -752,7 +832,8 @@ int bump_time_evals(bump_ctx* c, const double* theta, int iters, float* total_ms
     if (stream_ms) {   // the streaming kernel alone: events around each direct launch on the same stream
         float acc = 0.f;
         for (int i = 0; i < iters; ++i) {
-            DeviceChain chain(c, c->stream);
+            SlotGuard chain;
+            if (int r = chain.begin(c, c->stream)) return r;
             if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, c->ev0, c->ev1)) return r;
             CK(cudaEventSynchronize(c->ev1));
             float ms = 0.f;
@@ -769,7 +850,35 @@ int bump_ctx_flags(const bump_ctx* c) { return c ? (int)c->flags : -1; }
 
 int bump_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }   // for bump_nuts.cpp
 
-int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 5 : 4) : 0; }
+int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 4 : 3) : 0; }
+
+int bump_debug_timeline(bump_ctx* c, const double* theta, double* out_us, int64_t out_len) {
+    if (!theta || !out_us || out_len < 2 * TL_N) return fail(BUMP_E_INVALID, "bad timeline arguments");
+    if (int r = ensure_ready(c)) return r;
+    if (!c->d_timeline) CK(cudaMalloc(&c->d_timeline, sizeof(unsigned long long) * 2 * TL_N));
+    unsigned long long init[2 * TL_N], got[2 * TL_N];
+    for (int k = 0; k < TL_N; ++k) init[2 * k] = ~0ull, init[2 * k + 1] = 0ull;
+    const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
+    memcpy(c->h_theta, theta, sizeof(double) * nth);
+    CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    {
+        SlotGuard chain;
+        if (int r = chain.begin(c, c->stream)) return r;
+        if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, nullptr, nullptr, c->d_timeline)) return r;
+    }
+    CK(cudaMemcpyAsync(got, c->d_timeline, sizeof(got), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long t0 = ~0ull;
+    for (int k = 0; k < TL_N; ++k)
+        if (got[2 * k + 1] != 0ull) t0 = std::min(t0, got[2 * k]);
+    for (int k = 0; k < TL_N; ++k) {
+        const bool ran = got[2 * k + 1] != 0ull;
+        out_us[2 * k] = ran ? (double)(got[2 * k] - t0) * 1e-3 : -1.0;
+        out_us[2 * k + 1] = ran ? (double)(got[2 * k + 1] - t0) * 1e-3 : -1.0;
+    }
+    return BUMP_OK;
+}
 
 int bump_plan_info(bump_ctx* c, int64_t* info8) {
     if (!info8) return fail(BUMP_E_INVALID, "null info");

@@ -218,7 +218,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
     // The bucket table, keyed by the top bits of x, gives a lower bound b0 of the bin.  A bucket (1/256 octave) is
     // narrower than any bin of the d_L grid (log dl_{k+1} - log dl_k >= ZSTEP = 0.0045 > log(1 + 1/256)), so the
-    // bin is b0 or b0 + 1: one comparison with knot b0 + 1, no loop.  (records_kernel flags the evaluation as bad
+    // bin is b0 or b0 + 1: one comparison with knot b0 + 1, no loop.  (the prologue flags the evaluation as bad
     // if theta is so extreme that the ends of the bucket range break this: roughly h > 7 or h < 0.11; the prior is 0.35 .. 1.4.)
     int j = (__double2hiint(x) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
     j = min(max(j, 0), SRCH_N - 1);
@@ -357,7 +357,8 @@ __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ ou
 template <bool WA, bool FIXED, int SLOT>
 __global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
-              const double* __restrict__ g_blob, double* __restrict__ part) {
+              const double* __restrict__ g_blob, double* __restrict__ part, unsigned long long* __restrict__ tl) {
+    timeline_begin(tl, TL_STREAM);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int BLOB_BYTES = blob_doubles(WA, FIXED) * 8;   // the mode's share of the blob (bump_layout.cuh)
     double* s_blob = reinterpret_cast<double*>(smem_raw);
@@ -447,6 +448,7 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         e = e_next;
         k = k_next;
     }
+    if (tl != nullptr && lane == 0) atomicMax(tl + 2 * TL_STREAM + 1, global_ns());   // every warp: they finish apart
 }
 
 #undef K_SC

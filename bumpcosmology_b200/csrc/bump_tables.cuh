@@ -1,6 +1,12 @@
-// Prologue: theta-dependent tables with forward-mode tangents (tables_kernel), then the packed per-bin records
-// and scalars the streaming kernel bulk-copies into shared memory (records_kernel).
+// Prologue: ONE kernel per evaluation (prologue_kernel) builds the theta-dependent tables with forward-mode tangents
+// (256 PISN rows + 4 cosmology chunks, one block each, launched as thread-block clusters of 4) and then, in whichever
+// block finishes last, packs the per-bin records, the d_L bucket table and the scalars that the streaming kernel
+// bulk-copies into shared memory.  (Round 1 used two launches and a spin chain in global memory for the cumulative
+// trapezoid; the chain now runs over distributed shared memory inside the cosmology cluster, whose four blocks the
+// hardware co-schedules, so it cannot deadlock and needs no flag to re-arm.)
 #pragma once
+#include <cooperative_groups.h>
+
 #include "bump_dual.cuh"
 #include "bump_layout.cuh"
 
@@ -121,15 +127,16 @@ __device__ void pisn_row(const double* __restrict__ th, int i, double* __restric
 }
 
 // ---------------------------------------------------------------- cosmology tables (Dual<3>: Om, w, wa)
-// The 1024 knots are split over COS_CHUNKS blocks (one knot per thread): the single-block version was the critical
-// path of the whole prologue (13 us against 9 us for all 256 PISN rows).  The cumulative trapezoid crosses chunks
-// through a small chain in global memory (totals + flag per chunk); the chunks are the first blocks of the grid, so
-// they are resident together and a later chunk can safely wait for an earlier one.
+// The 1024 knots are split over COS_CHUNKS blocks (one knot per thread): a single block was the critical path of the
+// whole prologue.  The four chunks are the four blocks of ONE thread-block cluster (co-scheduled by the hardware):
+// the cumulative trapezoid crosses chunks through distributed shared memory - every block publishes its chunk total in
+// its own shared memory, one cluster barrier, then each block adds the totals of the chunks before it.
 constexpr int COS_CHUNKS = 4;
-constexpr int AUX_CHAIN_DOUBLES = COS_CHUNKS * 4;
 
 __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, double* __restrict__ aux, double* sm,
-                                 const int chunk, double* __restrict__ chain, unsigned int* __restrict__ chain_flag) {
+                                 const int chunk) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     typedef Dual<3> D;
     const int tid = chunk * PRO_THREADS + threadIdx.x;   // global knot-thread index
     const double h = th[T_H];
@@ -174,7 +181,7 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
         for (int c = 0; c < 4; ++c) sm[warp * 4 + c] = sc[c];
     }
     __syncthreads();
-    // chain across chunks: publish this chunk's total, then wait for the earlier chunks
+    // chain across chunks: publish this chunk's total in this block's shared memory (sm[72..75]) ...
     if (threadIdx.x == PRO_THREADS - 1) {
         // sc[] of the last thread of the last warp is that warp's inclusive total; add the earlier warps
         double t4[4] = {sc[0], sc[1], sc[2], sc[3]};
@@ -183,22 +190,20 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
             for (int c = 0; c < 4; ++c) t4[c] += sm[ww * 4 + c];
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) chain[chunk * 4 + c] = t4[c];
-        __threadfence();
-        atomicExch(chain_flag + chunk, 1u);
+        for (int c = 0; c < 4; ++c) sm[72 + c] = t4[c];
     }
+    cluster.sync();   // ... every chunk's total is now visible cluster-wide (release / acquire)
     if (threadIdx.x == 0) {
         double p4[4] = {0, 0, 0, 0};
-        for (int cc = 0; cc < chunk; ++cc) {
-            while (atomicAdd(chain_flag + cc, 0u) == 0u) {}
-            __threadfence();
+        for (int cc = 0; cc < chunk; ++cc) {   // chunk == rank of this block in its cluster (blocks 0..3 of the grid)
+            const double* peer = cluster.map_shared_rank(sm + 72, cc);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) p4[c] += __ldcg(chain + cc * 4 + c);
+            for (int c = 0; c < 4; ++c) p4[c] += peer[c];
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) sm[64 + c] = p4[c];
     }
-    __syncthreads();
+    cluster.sync();   // no block may exit (and release its shared memory) while a peer still reads its total
     double base[4] = {sm[64], sm[65], sm[66], sm[67]};
     for (int ww = 0; ww < warp; ++ww) {
 #pragma unroll
@@ -325,20 +330,96 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
     scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
 
-// ---------------------------------------------------------------- kernel 1: raw tables with tangents
-//   blocks 0..3        : flat wCDM distance tables, 256 knots each (intensity_models.py:229-235 + utils.py:3-8)
+// ---------------------------------------------------------------- packed records (last block of the prologue)
+// One item per thread and step: NZ cosmology bins, NM mass bins, NZ - 1 knots of the d_L bucket table (the exp table
+// of the blob is theta-independent and written once at context creation).  Runs in warps 1..7 of the block while warp
+// 0 derives the scalars.  aux was written by other blocks of this launch: read through L2.
+__device__ void pack_records(const double* __restrict__ aux_, double* __restrict__ blob, const EvalConsts ec,
+                             const int t /* 0 .. nt-1 */, const int nt) {
+    const CgView aux{aux_};
+    double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
+    double* ctan = blob + OFF_CTAN;
+    for (int b = t; b < NZ; b += nt) {
+        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
+        const CgView dl = aux + AUX_DL, dvc = aux + AUX_DVC, ddl = aux + AUX_DDL;
+        const double dl0 = dl[b0], dl1 = dl[b1];
+        cos[CR_DL * NZ + b] = make_double2(dl0, 1.0 / (dl1 - dl0));
+        const double v0 = dvc[b0], d0 = ddl[b0];
+        cos[CR_DVC * NZ + b] = make_double2(v0, dvc[b1] - v0);
+        cos[CR_DDL * NZ + b] = make_double2(d0, ddl[b1] - d0);
+        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), b0 * ZSTEP);
+        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
+        // pairs {t_b, t_{b+1} - t_b} otherwise (bump_layout.cuh), nothing in fixed-cosmology mode
+        const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
+        if (!ec.fixed) {
+            if (ec.use_wa) {
+#pragma unroll
+                for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
+            } else {
+                double2* ctan2 = reinterpret_cast<double2*>(ctan);
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    if (r % 3 == 2) continue;   // the wa tangents
+                    const CgView tt = aux + (AUX_TAN + r * NZ);
+                    const double t0 = tt[b0];
+                    ctan2[dst[r] * NZ + b] = make_double2(t0, tt[b1] - t0);
+                }
+            }
+        }
+        // ---- bucket table of the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j, i.e.
+        // for the smallest double x0_j of the bucket: clip(#{k < NZ-1 : dl_k <= x0_j}, 1, .) - 1.  Knot b owns the
+        // buckets whose x0_j lies in [dl_b, dl_{b+1}) (the last knot up to +inf): filled without any search.
+        if (!ec.fixed && b <= NZ - 2) {
+            unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
+            auto first_bucket_at_or_above = [](const double v) -> int {   // min{j : x0_j >= v}, clamped to [0, SRCH_N]
+                if (!(v > 0.0)) return 0;
+                const int key = (__double2hiint(v) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
+                if (key < 0) return 0;
+                if (key >= SRCH_N) return SRCH_N;
+                const bool exact = __double2loint(v) == 0 && (__double2hiint(v) & ((1 << (20 - SRCH_MBITS)) - 1)) == 0;
+                return exact ? key : key + 1;
+            };
+            const int j0 = (b == 0) ? 0 : first_bucket_at_or_above(dl0);
+            const int j1 = (b == NZ - 2) ? SRCH_N : first_bucket_at_or_above(dl1);
+            for (int j = j0; j < j1; ++j) srch[j] = (unsigned short)(j == 0 ? 0 : b);
+        }
+    }
+    double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
+    for (int item = t; item < NM; item += nt) {
+        const int b0 = min(item, NM - 2), b1 = b0 + 1;
+#pragma unroll
+        for (int r = 0; r < NMREC; ++r) {
+            const CgView g = aux + (AUX_G + r * NM);
+            const double g0 = g[b0];
+            mass[r * NM + item] = make_double2(g0, g[b1] - g0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the prologue kernel
+//   blocks 0..3        : flat wCDM distance tables, 256 knots each (intensity_models.py:229-235 + utils.py:3-8); they
+//                        are one cluster and chain their cumulative trapezoid through distributed shared memory
 //   blocks 4..4+NM-1   : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
-__global__ void __launch_bounds__(PRO_THREADS)
-tables_kernel(const double* __restrict__ theta, double* __restrict__ aux, unsigned int* __restrict__ flags,
-              const int use_wa, double* __restrict__ chain, unsigned int* __restrict__ chain_flag) {
+//   the block that finishes last (ticket): packed records + d_L bucket table (warps 1..7) and the scalars
+//                        (intensity_models.py:134-138,167-168; 7 threads of warp 0) -> the blob the streaming kernel stages
+constexpr int PRO_BLOCKS = NM + COS_CHUNKS;
+static_assert(PRO_BLOCKS % COS_CHUNKS == 0, "the grid is a whole number of clusters");
+
+__global__ void __cluster_dims__(COS_CHUNKS, 1, 1) __launch_bounds__(PRO_THREADS)
+prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
+                unsigned int* __restrict__ flags /* [0] ticket, [1] bad */, const EvalConsts ec,
+                unsigned long long* __restrict__ tl) {
     __shared__ double sm[9 * NM + 64];
     __shared__ double th[NTHETA_MAX];
+    __shared__ bool is_last;
+    timeline_begin(tl, TL_PROLOGUE);
+    const int use_wa = ec.use_wa;
     if (threadIdx.x < NTHETA_MAX) th[threadIdx.x] = (threadIdx.x < NTHETA || use_wa) ? theta[threadIdx.x] : 0.0;
     __syncthreads();
     const bool is_cos = blockIdx.x < COS_CHUNKS;    // cosmology chunks first: they are the longer chains
     const int row = (int)blockIdx.x - COS_CHUNKS;
     if (!is_cos) pisn_row(th, row, aux, sm);
-    else cosmology_tables(th, use_wa, aux, sm, blockIdx.x, chain, chain_flag);
+    else cosmology_tables(th, use_wa, aux, sm, blockIdx.x);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     int bad = 0;
     __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
@@ -349,26 +430,25 @@ tables_kernel(const double* __restrict__ theta, double* __restrict__ aux, unsign
         for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1u);
-}
-
-// ---------------------------------------------------------------- kernel 2: packed records + scalars
-// One item per thread: NZ cosmology bins, NM mass bins, SRCH_N d_L buckets (the exp table of the blob is
-// theta-independent and written once at context creation); the extra last block derives the scalars (intensity_models.py:134-138,167-168) from a shared-memory copy of the PISN table.
-constexpr int REC_ITEMS = NZ + NM + SRCH_N;
-constexpr int REC_BLOCKS = (REC_ITEMS + PRO_THREADS - 1) / PRO_THREADS;   // + 1 block for the scalars
-
-__global__ void __launch_bounds__(PRO_THREADS)
-records_kernel(const double* __restrict__ theta, const double* __restrict__ aux, double* __restrict__ blob,
-               unsigned int* __restrict__ flags, const EvalConsts ec, unsigned int* __restrict__ chain_flag) {
-    __shared__ double sm[6 * NM];
-    if (blockIdx.x == REC_BLOCKS) {
-        for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) sm[k] = aux[AUX_G + k];
-        __syncthreads();
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
+    // ---- last block: everything the other blocks wrote is visible after the ticket
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(flags, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) {
+        timeline_end(tl, TL_PROLOGUE);
+        return;
+    }
+    __threadfence();
+    double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
+    for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
+    __syncthreads();
+    if (threadIdx.x < 32) {
         if (threadIdx.x < 7) {
-            double th[NTHETA_MAX];
-            for (int k = 0; k < NTHETA_MAX; ++k) th[k] = (k < NTHETA || ec.use_wa) ? theta[k] : 0.0;
-            build_scalars(th, aux, sm, ec, blob + OFF_SCAL, threadIdx.x);
+            double thr[NTHETA_MAX];
+            for (int k = 0; k < NTHETA_MAX; ++k) thr[k] = th[k];
+            build_scalars(thr, aux, gtab, ec, blob + OFF_SCAL, threadIdx.x);
         }
         if (threadIdx.x == 0) {
             // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
@@ -377,74 +457,16 @@ records_kernel(const double* __restrict__ theta, const double* __restrict__ aux,
             // last two bins).  That takes roughly h > 7 or h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).
             const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
             const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
-            if (!ec.fixed && (!(aux[AUX_DL + 2] >= first_hi) || !(aux[AUX_DL + NZ - 3] <= last_lo))) *flags = 1u;
-            blob[OFF_SCAL + S_BAD] = (*flags != 0u) ? 1.0 : 0.0;
-            *flags = 0u;
-            for (int cc = 0; cc < COS_CHUNKS; ++cc) chain_flag[cc] = 0u;   // re-arm the scan chain of tables_kernel
+            unsigned int f = flags[1];
+            if (!ec.fixed && (!(__ldcg(aux + AUX_DL + 2) >= first_hi) || !(__ldcg(aux + AUX_DL + NZ - 3) <= last_lo))) f = 1u;
+            blob[OFF_SCAL + S_BAD] = (f != 0u) ? 1.0 : 0.0;
+            flags[0] = 0u;   // re-arm the ticket and the bad flag for the next evaluation
+            flags[1] = 0u;
         }
-        return;
+    } else {
+        pack_records(aux, blob, ec, threadIdx.x - 32, PRO_THREADS - 32);
     }
-    double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
-    double* ctan = blob + OFF_CTAN;
-    int item = blockIdx.x * PRO_THREADS + threadIdx.x;
-    const bool need_dl = (blockIdx.x + 1) * PRO_THREADS > NZ + NM;   // this block holds d_L bucket items
-    if (need_dl) {
-        for (int k = threadIdx.x; k < NZ; k += PRO_THREADS) sm[k] = aux[AUX_DL + k];
-        __syncthreads();
-    }
-    if (item < NZ) {
-        const int b = item, b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
-        const double* dl = aux + AUX_DL;
-        const double* dvc = aux + AUX_DVC;
-        const double* ddl = aux + AUX_DDL;
-        cos[CR_DL * NZ + b] = make_double2(dl[b0], 1.0 / (dl[b1] - dl[b0]));
-        cos[CR_DVC * NZ + b] = make_double2(dvc[b0], dvc[b1] - dvc[b0]);
-        cos[CR_DDL * NZ + b] = make_double2(ddl[b0], ddl[b1] - ddl[b0]);
-        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), b0 * ZSTEP);
-        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
-        // pairs {t_b, t_{b+1} - t_b} otherwise (bump_layout.cuh), nothing in fixed-cosmology mode
-        const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
-        if (ec.fixed) return;
-        if (ec.use_wa) {
-#pragma unroll
-            for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
-        } else {
-            double2* ctan2 = reinterpret_cast<double2*>(ctan);
-#pragma unroll
-            for (int r = 0; r < 9; ++r) {
-                if (r % 3 == 2) continue;   // the wa tangents
-                const double* t = aux + AUX_TAN + r * NZ;
-                ctan2[dst[r] * NZ + b] = make_double2(t[b0], t[b1] - t[b0]);
-            }
-        }
-        return;
-    }
-    item -= NZ;
-    if (item < NM) {
-        double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
-        const int b0 = min(item, NM - 2), b1 = b0 + 1;
-#pragma unroll
-        for (int r = 0; r < NMREC; ++r) {
-            const double* g = aux + AUX_G + r * NM;
-            mass[r * NM + item] = make_double2(g[b0], g[b1] - g[b0]);
-        }
-        return;
-    }
-    item -= NM;
-    if (item < SRCH_N) {
-        // bucket table for the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j
-        unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
-        const int key = item + (SRCH_EXP_LO << SRCH_MBITS);
-        const double x0 = __hiloint2double(key << (20 - SRCH_MBITS), 0);   // smallest double of the bucket
-        int pos = 0;                                                        // #{k < NZ-1 : dl_k <= x0}
-#pragma unroll
-        for (int step = NZ / 2; step >= 1; step >>= 1) {
-            if (sm[pos + step - 1] <= x0) pos += step;
-        }
-        const int b = min(max(pos, 1) - 1, NZ - 2);
-        srch[item] = (unsigned short)(item == 0 ? 0 : b);
-        return;
-    }
+    timeline_end(tl, TL_PROLOGUE);
 }
 
 }  // namespace bump

@@ -114,6 +114,7 @@ class Hyperlikelihood:
         self._out = np.empty(int(self.lib.bump_out_len(self._ctx)), dtype=np.float64)
         self._theta = np.zeros(_lib.NTHETA_MAX, dtype=np.float64)
         self._out_p, self._theta_p = _lib.as_dp(self._out), _lib.as_dp(self._theta)
+        self.plan()   # builds the execution plan now: every later call (also inside a stream capture) allocates nothing
 
     # -- lifetime
     def close(self):
@@ -194,6 +195,15 @@ class Hyperlikelihood:
                                             C.byref(ker) if kernel else None))
         return tot.value, (ker.value if kernel else None)
 
+    def timeline(self, theta):
+        """Per-kernel timeline of one evaluation launched directly (no graph): {kernel: (start_us, end_us)} on the
+        GPU's global timer, relative to the first kernel's first block."""
+        th = self._set_theta(theta)
+        buf = np.empty(8)
+        _lib.check(self.lib.bump_debug_timeline(self._ctx, _lib.as_dp(th), _lib.as_dp(buf), 8))
+        names = ("prologue", "stream", "epilogue", "finalize")
+        return {n: (float(buf[2 * i]), float(buf[2 * i + 1])) for i, n in enumerate(names) if buf[2 * i + 1] >= 0}
+
     def plan(self):
         info = (C.c_int64 * 8)()
         _lib.check(self.lib.bump_plan_info(self._ctx, info))
@@ -225,7 +235,7 @@ class ShardedHyperlikelihood:
                          peer's mailbox over NVLink (cudaIpc-mapped peer memory) and merges (bump_p2p_attach)
     """
 
-    def __init__(self, data, device=None, wa=False, exchange="p2p", group=None):
+    def __init__(self, data, device=None, wa=False, exchange="p2p", group=None, timeout_s=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -253,6 +263,8 @@ class ShardedHyperlikelihood:
             dist.all_gather_into_tensor(allh, mine, group=group)
             hb = allh.cpu().numpy().tobytes()
             buf = (C.c_char * len(hb)).from_buffer_copy(hb)
+            if timeout_s is not None:   # how long a rank waits for a peer's partial before the evaluation fails everywhere
+                ok = ok and lib.bump_p2p_set_timeout(ctx, float(timeout_s)) == 0
             ok = ok and lib.bump_p2p_attach(ctx, buf, self.world, self.rank) == 0
             flag = torch.tensor([1 if ok else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
@@ -284,7 +296,12 @@ class ShardedHyperlikelihood:
     def raw(self, theta):
         return self.local.raw(theta) if self.exchange in ("nccl", "p2p") else None
 
+    def close(self):
+        self.local.close()
+
     def __call__(self, theta):
+        """A failed peer-memory exchange (a rank did not arrive within the timeout) raises BumpError with code
+        _lib.E_EXCHANGE on EVERY rank - never a result on some ranks and an error on others."""
         if self.exchange in ("nccl", "p2p"):   # the exchange lives inside the library's CUDA graph
             return self.local(theta)
         th = np.asarray(theta, dtype=np.float64).ravel()

@@ -34,6 +34,8 @@ extern "C" {
 #define BUMP_OUT_NVALID_SEL 35  /* number of injections with finite weight (diagnostic) */
 #define BUMP_OUT_NOBS 36        /* total number of events over all ranks */
 #define BUMP_OUT_NSEL 37        /* total number of found injections over all ranks */
+#define BUMP_OUT_STATUS 38      /* 0 = ok; 1 / 2 = the multi-rank peer-memory exchange timed out / was poisoned by a
+                                 * failing peer (outputs are NaN then, on EVERY rank; bump_eval returns BUMP_E_EXCHANGE) */
 #define BUMP_OUT_HEADER 40      /* neff[nobs_local] follows (intensity_models.py:401) */
 
 /* Per-rank partial for the multi-GPU exchange (doubles); see DESIGN.md "multi-GPU". */
@@ -44,6 +46,8 @@ extern "C" {
 #define BUMP_E_CUDA 2      /* CUDA runtime error (message has the cudaError string) */
 #define BUMP_E_NOGPU 3     /* no CUDA device: there is NO CPU fallback */
 #define BUMP_E_NCCL 4      /* NCCL missing or failed */
+#define BUMP_E_EXCHANGE 5  /* the peer-memory exchange of a multi-rank evaluation failed (timeout / poisoned): the
+                            * evaluation did not happen on ANY rank; detach, synchronise the ranks, attach again */
 
 /* Evaluation flags (bump_ctx_create). */
 #define BUMP_FLAG_WA 1u        /* w0-wa (CPL) dark energy: theta has 15 entries */
@@ -91,7 +95,12 @@ int64_t bump_out_len(const bump_ctx* ctx);
 int bump_eval(bump_ctx* ctx, const double* theta, double* out);
 
 /* Same, fully asynchronous on a caller stream with DEVICE pointers (what an XLA FFI handler calls):
- * no allocation, no host synchronisation.  stream is a cudaStream_t passed as void*. */
+ * no allocation, no host synchronisation.  stream is a cudaStream_t passed as void*.  The stream may be CAPTURING
+ * (an XLA command buffer, torch.cuda.graph): the evaluation then becomes 3 kernel nodes and one 512-byte copy node of
+ * the caller's graph.  Capture needs (a) the plan built beforehand (bump_plan_info or one evaluation after the uploads)
+ * and (b) a context that owns its constant-bank slot alone, i.e. at most 4 contexts alive on the device; the slot
+ * stays reserved for the captured context until it is destroyed.  A context is not re-entrant: do not run two of its
+ * evaluations (captured or not) concurrently.  out_dev[BUMP_OUT_STATUS] reports a failed multi-rank exchange. */
 int bump_eval_device(bump_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
 
 /* Multi-GPU, host-driven exchange (torch.distributed or any allgather): produce this rank's partial
@@ -120,11 +129,16 @@ int bump_comm_attach(bump_ctx* ctx, const void* id128, int nranks, int rank);
  * flag, waits for the peers' flags and merges — no NCCL call and no extra launch on the evaluation path.
  * bump_p2p_export writes this rank's 64-byte cudaIpcMemHandle_t; the host all-gathers the handles (any transport)
  * and passes the [nranks][64] array to bump_p2p_attach.  At most 16 ranks.  Every rank must then call bump_eval /
- * bump_eval_device the same number of times (it is a collective); a peer that never arrives makes the others return
- * NaN after ~10 s instead of hanging the GPU. */
+ * bump_eval_device the same number of times (it is a collective).  A peer that does not arrive within the timeout
+ * (default 10 s; bump_p2p_set_timeout or the environment variable BUMP_P2P_TIMEOUT_S) makes the evaluation FAIL ON
+ * EVERY RANK, the late one included: the waiting ranks give up, poison their flags in all peer mailboxes and mark
+ * their exchange broken; bump_eval returns BUMP_E_EXCHANGE (bump_eval_device: out[BUMP_OUT_STATUS] != 0, NaN outputs)
+ * from then on until every rank has called bump_p2p_detach, the ranks have synchronised on the host, and the mailboxes
+ * are exported and attached again.  No rank ever sees a result that another rank did not also see. */
 int bump_p2p_export(bump_ctx* ctx, void* handle64);
 int bump_p2p_attach(bump_ctx* ctx, const void* handles, int nranks, int rank);
 int bump_p2p_detach(bump_ctx* ctx);   /* back to a single-rank context (e.g. to fall back to bump_comm_attach) */
+int bump_p2p_set_timeout(bump_ctx* ctx, double seconds);
 
 /* Introspection for unit-level parity tests of the prologue kernels (F1-F3 of SURVEY.md section 2.2):
  * copies the theta-dependent tables of the last evaluation to the host.
@@ -139,6 +153,11 @@ int bump_debug_tables(bump_ctx* ctx, int which, double* out, int64_t out_len);
  * stream_ms is non-NULL, the milliseconds spent in the streaming kernel alone (events around each launch,
  * graph replay disabled for that measurement). */
 int bump_time_evals(bump_ctx* ctx, const double* theta, int iters, float* total_ms, float* stream_ms);
+
+/* Per-kernel timeline of ONE evaluation launched directly (no graph): out_us[2k], out_us[2k+1] = start of the first
+ * block / end of the last block of kernel k (0 prologue, 1 streaming, 2 epilogue, 3 finalize; -1 if it did not run)
+ * in microseconds on the GPU's global timer, relative to the start of the first kernel.  out_len >= 8. */
+int bump_debug_timeline(bump_ctx* ctx, const double* theta, double* out_us, int64_t out_len);
 
 /* Number of kernel launches one bump_eval performs (for bench.py's gpu_launches). */
 int bump_launches_per_eval(const bump_ctx* ctx);

@@ -20,11 +20,10 @@
 #include <algorithm>
 #include <vector>
 
-#define __host__
-#define __device__
-#include "../bumpcosmology_b200/csrc/bump_dual.cuh"   // forward-mode dual numbers (host + device header)
+#include "cpu_dual.h"   // the oracle's own forward-mode derivatives (no source shared with the CUDA library)
 
-using bump::Dual;
+template <int N>
+using Dual = cpuad::Fwd<N>;
 
 namespace {
 
@@ -51,7 +50,7 @@ void build_tables(const double* th, Tables& T) {
     // ---- flat wCDM tables with tangents (:229-235, utils.py:3-8)
     {
         typedef Dual<2> D;
-        const D Om = D::var(th[T_OM], 0), w = D::var(th[T_W], 1);
+        const D Om = D::seed(th[T_OM], 0), w = D::seed(th[T_W], 1);
         const double dH = C_H100_GPC / th[T_H];
         const double step = log1p(ZMAX) / (NZ - 1);
         std::vector<D> iE(NZ);
@@ -59,31 +58,31 @@ void build_tables(const double* th, Tables& T) {
             const double lz = (k == NZ - 1) ? log1p(ZMAX) : k * step;
             T.z[k] = expm1(lz);
             const double opz = 1.0 + T.z[k];
-            D de = bump::dexp((3.0 * (1.0 + w)) * log(opz));
-            D E = bump::dsqrt(Om * (opz * opz * opz) + (1.0 - Om) * de);
+            D de = cpuad::exp((3.0 * (1.0 + w)) * log(opz));
+            D E = cpuad::sqrt(Om * (opz * opz * opz) + (1.0 - Om) * de);
             iE[k] = 1.0 / E;
         }
         D C(0.0);
         for (int k = 0; k < NZ; ++k) {
             if (k > 0) C = C + (0.5 * (T.z[k] - T.z[k - 1])) * (iE[k - 1] + iE[k]);
             const double opz = 1.0 + T.z[k];
-            D dc = dH * C, dl = dc * opz, ddl = dc + (dH * opz) * iE[k], dvc = (FOUR_PI * dH) * (bump::dsquare(dc) * iE[k]);
+            D dc = dH * C, dl = dc * opz, ddl = dc + (dH * opz) * iE[k], dvc = (FOUR_PI * dH) * (cpuad::square(dc) * iE[k]);
             T.dl[k] = dl.v, T.ddl[k] = ddl.v, T.dvc[k] = dvc.v;
             for (int c = 0; c < 2; ++c) T.t_dl[c][k] = dl.d[c], T.t_ddl[c][k] = ddl.d[c], T.t_dvc[c][k] = dvc.d[c];
         }
     }
     // ---- PISN table (:96-108), one row per iteration
     typedef Dual<5> D5;
-    const D5 a = D5::var(th[T_A], 0), b = D5::var(th[T_B], 1), mpisn = D5::var(th[T_MPISN], 2),
-             M = D5::var(th[T_MBHMAX], 3), sg = D5::var(th[T_SIGMA], 4);
-    const D5 top = M + 7.0 * sg, mcomax = 2.0 * M - mpisn, mco_top = mcomax + bump::dsqrt(4.0 * M * (M - mpisn));
+    const D5 a = D5::seed(th[T_A], 0), b = D5::seed(th[T_B], 1), mpisn = D5::seed(th[T_MPISN], 2),
+             M = D5::seed(th[T_MBHMAX], 3), sg = D5::seed(th[T_SIGMA], 4);
+    const D5 top = M + 7.0 * sg, mcomax = 2.0 * M - mpisn, mco_top = mcomax + cpuad::sqrt(4.0 * M * (M - mpisn));
     const D5 alpha = 1.0 / (4.0 * (mpisn - M));
     std::vector<D5> mco(NM), ell(NM), mu(NM);
     for (int j = 0; j < NM; ++j) {
         const double sj = (double)j / (NM - 1);
         mco[j] = (j == NM - 1) ? mco_top : (MIN_CO_MASS * (1.0 - sj) + mco_top * sj);
-        mu[j] = (mco[j].v < mpisn.v) ? mco[j] : (M + alpha * bump::dsquare(mco[j] - mcomax));
-        D5 lx = bump::dlog(mco[j] / MTR);
+        mu[j] = (mco[j].v < mpisn.v) ? mco[j] : (M + alpha * cpuad::square(mco[j] - mcomax));
+        D5 lx = cpuad::log(mco[j] / MTR);
         ell[j] = (mco[j].v < MTR) ? (-a * lx) : (-b * lx);
     }
 #pragma omp parallel for schedule(static)
@@ -93,12 +92,12 @@ void build_tables(const double* th, Tables& T) {
         D5 lw[NM];
         for (int j = 0; j < NM; ++j) {
             D5 u = (mbh - mu[j]) / sg;
-            lw[j] = ell[j] - 0.5 * bump::dsquare(u) - HALF_LOG_2PI - bump::dlog(sg);
+            lw[j] = ell[j] - 0.5 * cpuad::square(u) - HALF_LOG_2PI - cpuad::log(sg);
         }
         D5 term[NM - 1];
         double mx = -INFINITY;
         for (int j = 0; j < NM - 1; ++j) {
-            term[j] = bump::dlogaddexp(lw[j + 1], lw[j]) + bump::dlog(mco[j + 1] - mco[j]) - LN2;
+            term[j] = cpuad::logaddexp(lw[j + 1], lw[j]) + cpuad::log(mco[j + 1] - mco[j]) - LN2;
             mx = fmax(mx, term[j].v);
         }
         double s = 0.0, sd[5] = {0, 0, 0, 0, 0};
@@ -113,8 +112,8 @@ void build_tables(const double* th, Tables& T) {
     // ---- scalars (:134-138, :167-168)
     typedef Dual<7> D7;   // a, b, c, mpisn, mbhmax, sigma, fpl
     const int map5[5] = {0, 1, 3, 4, 5};
-    const D7 c7 = D7::var(th[T_C], 2), M7 = D7::var(th[T_MBHMAX], 4), sg7 = D7::var(th[T_SIGMA], 5),
-             fpl7 = D7::var(th[T_FPL], 6);
+    const D7 c7 = D7::seed(th[T_C], 2), M7 = D7::seed(th[T_MBHMAX], 4), sg7 = D7::seed(th[T_SIGMA], 5),
+             fpl7 = D7::seed(th[T_FPL], 6);
     const D7 top7 = M7 + 7.0 * sg7;
     auto knot = [&](int k) -> D7 {
         const double s = (double)k / (NM - 1);
@@ -134,12 +133,12 @@ void build_tables(const double* th, Tables& T) {
         if (m.v > top7.v) f = Gk(NM - 1);
         return f;
     };
-    const D7 lpn = bump::dlog(fpl7) + pisn(M7);
+    const D7 lpn = cpuad::log(fpl7) + pisn(M7);
     const D7 mref(MREF);
     const D7 P = (MREF <= MIN_BH_MASS || MREF >= top7.v) ? D7(-INFINITY) : pisn(mref);
-    const D7 turn = LN2 - bump::dlog1p(bump::dexp(-(mref - M7) / (M7 * TURNON_WIDTH)));
-    const D7 Q = -c7 * bump::dlog(mref / M7) + lpn + turn;
-    const D7 ln = -(bump::dlogaddexp(P, Q) + log(MREF));
+    const D7 turn = LN2 - cpuad::log1p(cpuad::exp(-(mref - M7) / (M7 * TURNON_WIDTH)));
+    const D7 Q = -c7 * cpuad::log(mref / M7) + lpn + turn;
+    const D7 ln = -(cpuad::logaddexp(P, Q) + log(MREF));
     const double kappa = th[T_KAPPA], zp = th[T_ZP], lopzp = log1p(zp);
     const double r0 = exp(-kappa * lopzp), sig0 = r0 / (1.0 + r0);
     T.top = top7.v, T.inv_dmbh = (NM - 1) / (top7.v - MIN_BH_MASS), T.M = M7.v, T.logM = log(M7.v);
