@@ -46,6 +46,7 @@ SIGNATURES = {
     "bump_p2p_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "bump_debug_timeline": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64]),
     "bump_debug_tables": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64]),
+    "bump_debug_math": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]),
     "bump_time_evals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bump_launches_per_eval": (C.c_int, [C.c_void_p]),
     "bump_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

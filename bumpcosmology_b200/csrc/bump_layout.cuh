@@ -43,10 +43,23 @@ constexpr int SRCH_OCTAVES = 21;          // 2^-8 .. 2^13 Gpc
 constexpr int SRCH_N = SRCH_OCTAVES << SRCH_MBITS;   // 5376 uint16 entries
 constexpr int SRCH_DOUBLES = SRCH_N / 4;
 
-constexpr int NEXPT = 2048;  // 2^(j/2048) (bump_math.cuh fexp); theta-independent, written once per context
+// exp table (bump_math.cuh fexp): 2^(j/NEXPT), theta-independent, written once per context.  Each entry is stored
+// EXPT_REPL times in a row and lane l reads copy (l mod EXPT_REPL): the 32 lanes of a lookup at random j then spread
+// over the banks by construction (EXPT_REPL = 16: each of the 16 64-bit bank pairs serves exactly two lanes = the
+// minimum of 2 wavefronts; one copy of a 2048-entry table: ~6).  A shorter table needs a longer polynomial.
+#ifndef BUMP_EXPT_LOG2
+#define BUMP_EXPT_LOG2 11
+#endif
+#ifndef BUMP_EXPT_REPL_LOG2
+#define BUMP_EXPT_REPL_LOG2 0
+#endif
+constexpr int NEXPT = 1 << BUMP_EXPT_LOG2;
+constexpr int EXPT_REPL = 1 << BUMP_EXPT_REPL_LOG2;
+constexpr int EXPT_DOUBLES = NEXPT * EXPT_REPL;
+static_assert(EXPT_REPL <= 16, "16 bank pairs");
 constexpr int OFF_SCAL = 0;
-constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT]
-constexpr int OFF_COS = OFF_EXPT + NEXPT;               // double2 cos[NCPAIR][NZ]
+constexpr int OFF_EXPT = OFF_SCAL + NSCAL;              // double  expt[NEXPT][EXPT_REPL]
+constexpr int OFF_COS = OFF_EXPT + EXPT_DOUBLES;        // double2 cos[NCPAIR][NZ]
 constexpr int OFF_SRCH = OFF_COS + NCPAIR * NZ * 2;     // uint16  srch[SRCH_N]
 constexpr int OFF_MASS = OFF_SRCH + SRCH_DOUBLES;       // double2 mass[NMREC][NM]
 // The cosmology tangent tables come last because their format depends on the mode (227 KB of shared memory do not
@@ -62,7 +75,8 @@ __host__ __device__ constexpr int blob_doubles(const bool wa, const bool fixed) 
 constexpr int BLOB_DOUBLES_MAX = OFF_CTAN + NCTAN_PAIR * NZ * 2;
 constexpr int BLOB_BYTES_MAX = BLOB_DOUBLES_MAX * 8;
 static_assert(blob_doubles(true, false) <= BLOB_DOUBLES_MAX, "the pair layout is the largest blob");
-static_assert(BLOB_BYTES_MAX + 16 <= 227 * 1024, "the blob (+ mbarrier) must fit the 227 KB of shared memory per CTA");
+static_assert(BLOB_BYTES_MAX <= 227 * 1024, "the blob must fit the 227 KB of shared memory per CTA (the streaming "
+                                            "kernel's mbarrier sits in the unused scalar block at its start)");
 static_assert(OFF_CTAN % 2 == 0 && (blob_doubles(false, false) % 2) == 0 && (blob_doubles(true, false) % 2) == 0,
               "bulk copies need 16-byte multiples");
 static_assert(SRCH_N % 4 == 0, "search table must fill whole doubles");

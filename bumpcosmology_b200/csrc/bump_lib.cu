@@ -123,7 +123,8 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
     const int64_t total = nrows * stride;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / stride, c = i - r * stride;
-        if (c < ncols) {
+        bool sentinel = c >= ncols;
+        if (!sentinel) {
             int64_t s = r * ncols + c;
             if (perm) s = perm[s];
             const double vm = m1d[s], vq = q[s];
@@ -131,6 +132,10 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
             if (!(vm > 0.0 && vq > 0.0 && dl[s] > 0.0 && pd[s] > 0.0 && isfinite(vm) && isfinite(vq) &&
                   isfinite(dl[s]) && isfinite(pd[s])))
                 atomicOr(bad, 1u);
+            // A sample whose DETECTOR-frame secondary is already below mbh_min has m2 = q m1_det / (1+z) < 5 at every
+            // redshift: its weight is zero for every theta (intensity_models.py:149).  Storing a sentinel instead lets
+            // the streaming kernel drop all range guards: what it sees always has m1 >= m2 >= 5/101.
+            if (vq * vm < MBH_MIN || vm < MBH_MIN) sentinel = true;
             out[block_index(i, C_M1D)] = vm;
             out[block_index(i, C_Q)] = vq;
             out[block_index(i, C_LM)] = log(vm);
@@ -151,9 +156,10 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
                 if (z > z1 && k == NZ - 2) v = fixed_tab[NZ - 1];
                 out[block_index(i, C_DL)] = lz;
                 out[block_index(i, C_LPD)] = log(pd[s]) - log(v);
-                if (!(v > 0.0)) out[block_index(i, C_M1D)] = 1.0;   // log dVdzdt = -inf: zero weight (sentinel mass)
+                if (!(v > 0.0)) sentinel = true;   // log dVdzdt = -inf: zero weight
             }
-        } else {   // sentinel padding: source mass 1/(1+z) < mbh_min -> weight exactly zero (-inf log weight)
+        }
+        if (sentinel) {   // padding / never-valid sample: source mass 1/(1+z) < mbh_min -> weight exactly zero (-inf log weight)
             out[block_index(i, C_DL)] = 1.0;
             out[block_index(i, C_M1D)] = 1.0;
             out[block_index(i, C_Q)] = 1.0;
@@ -162,6 +168,30 @@ __global__ void prepare_columns_kernel(const double* __restrict__ m1d, const dou
             out[block_index(i, C_L1Q)] = LN2;
             out[block_index(i, C_LPD)] = 0.0;
         }
+    }
+}
+
+// Accuracy probe of the streaming kernel's scalar math (bump_debug_math): y[i] = f(x[i]) with the exp table staged
+// exactly where the kernel expects it.
+__global__ void math_probe_kernel(const int which, const double* __restrict__ x, const int64_t n,
+                                  const double* __restrict__ g_blob, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char probe_smem[];
+    double* s = reinterpret_cast<double*>(probe_smem);
+    for (int k = threadIdx.x; k < EXPT_DOUBLES; k += blockDim.x) s[OFF_EXPT + k] = g_blob[OFF_EXPT + k];
+    __syncthreads();
+    const uint32_t sb = smem_u32(probe_smem);
+    const uint32_t rep = (uint32_t)(threadIdx.x & (EXPT_REPL - 1)) << 3;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        double r = 0.0;
+        switch (which) {
+            case 0: r = fexp<false>(v, sb, rep); break;
+            case 1: r = fexp<true>(v, sb, rep); break;
+            case 2: r = frcp(v); break;
+            case 3: r = flog1p_small(v); break;
+            default: r = frcp1p_small(v); break;
+        }
+        y[i] = r;
     }
 }
 
@@ -521,9 +551,10 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     CK(cudaMalloc(&c->d_blob, BLOB_BYTES_MAX));
     CK(cudaMemset(c->d_blob, 0, BLOB_BYTES_MAX));
     {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
-        std::vector<double> expt(NEXPT);
-        for (int j = 0; j < NEXPT; ++j) expt[j] = (double)exp2l((long double)j / NEXPT);
-        CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * NEXPT, cudaMemcpyHostToDevice));
+        std::vector<double> expt(EXPT_DOUBLES);
+        for (int j = 0; j < NEXPT; ++j)
+            for (int r = 0; r < EXPT_REPL; ++r) expt[j * EXPT_REPL + r] = (double)exp2l((long double)j / NEXPT);
+        CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * EXPT_DOUBLES, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
     // [0] unused, [1] epilogue ticket, [2] unused, [3] bad-input flag, [4] prologue ticket, [5] bad-theta flag
@@ -812,6 +843,24 @@ int bump_debug_tables(bump_ctx* c, int which, double* out, int64_t out_len) {
     if (out_len < n) return fail(BUMP_E_INVALID, "output buffer too small");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return BUMP_OK;
+}
+
+int bump_debug_math(bump_ctx* c, int which, const double* x, int64_t n, double* y) {
+    if (!c || !x || !y || n < 1 || which < 0 || which > 4) return fail(BUMP_E_INVALID, "bad math-probe arguments");
+    if (int r = set_device(c)) return r;
+    double *dx = nullptr, *dy = nullptr;
+    CK(cudaMalloc(&dx, sizeof(double) * n));
+    CK(cudaMalloc(&dy, sizeof(double) * n));
+    CK(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    const int smem = (OFF_EXPT + EXPT_DOUBLES) * 8;
+    CK(cudaFuncSetAttribute(math_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    math_probe_kernel<<<64, 256, smem, c->stream>>>(which, dx, n, c->d_blob, dy);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dy);
     return BUMP_OK;
 }
 

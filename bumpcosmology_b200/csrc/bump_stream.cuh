@@ -33,8 +33,10 @@ namespace bump {
 #endif
 constexpr int STREAM_THREADS = BUMP_STREAM_THREADS;
 constexpr int STREAM_WARPS = STREAM_THREADS / 32;
+// The blob is staged at its natural offsets, minus its first NSCAL doubles: the streaming kernel takes the scalars
+// from the constant bank, so their 512 bytes of shared memory hold the mbarrier instead.
 __host__ __device__ constexpr int stream_smem_bytes(const bool wa, const bool fixed) {
-    return blob_doubles(wa, fixed) * 8 + 16 /*mbarrier*/;
+    return blob_doubles(wa, fixed) * 8;
 }
 constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
@@ -50,7 +52,7 @@ __constant__ double K_SC4[NSLOT][NSCAL];
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int BLOB_BYTES>
+template <int BLOB_BYTES, int SKIP_BYTES>
 __device__ __forceinline__ void stage_tables(double* s_blob, uint64_t* mbar, const double* __restrict__ g_blob) {
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -59,10 +61,10 @@ __device__ __forceinline__ void stage_tables(double* s_blob, uint64_t* mbar, con
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
-                     "r"((uint32_t)BLOB_BYTES)
+                     "r"((uint32_t)(BLOB_BYTES - SKIP_BYTES))
                      : "memory");
         constexpr int CHUNK = 32768;
-        for (int off = 0; off < BLOB_BYTES; off += CHUNK) {
+        for (int off = SKIP_BYTES; off < BLOB_BYTES; off += CHUNK) {
             const int n = (BLOB_BYTES - off < CHUNK) ? (BLOB_BYTES - off) : CHUNK;
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -117,15 +119,18 @@ constexpr int COS_BYTES = OFF_COS * 8;
 constexpr int CTAN_BYTES = OFF_CTAN * 8;
 constexpr int SRCH_BYTES = OFF_SRCH * 8;
 
-// `sb` = shared-window address of the table blob
-template <int SLOT>
-__device__ __forceinline__ void mass_eval(const double m, const double lm, const uint32_t sb, MassEval& o) {
+// `sb` = shared-window address of the table blob.  SHIFTED: both exponents carry the extra term `d` (the sample's
+// lin - shift for the evaluation at m1, see eval_sample), i.e. the result is e^d (EP + EQ) at no extra exponential.
+template <int SLOT, bool SHIFTED>
+__device__ __forceinline__ void mass_eval(const double m, const double lm, const double d, const uint32_t sb,
+                                          const uint32_t rep, MassEval& o) {
     // -(m - M)/(0.05 M) = 20 - m/(0.05 M): one FMA
-    const double e = fexp<false>(fma(m, -K_SC[S_INV_DM], 1.0 / TURNON_WIDTH), sb);
+    const double e = fexp<false>(fma(m, -K_SC[S_INV_DM], 1.0 / TURNON_WIDTH), sb, rep);
     const double s1 = frcp(1.0 + e);
     o.sgm = (e * s1) * m;
     o.lrel = lm - K_SC[S_LOG_M];
-    o.EQ = fexp<false>(fma(o.lrel, -K_SC[S_C], K_SC[S_LOG_C2]), sb) * s1;   // 2 e^{lpn} (m/M)^-c / (1 + e)
+    const double cq = SHIFTED ? K_SC[S_LOG_C2] + d : K_SC[S_LOG_C2];
+    o.EQ = fexp<false>(fma(o.lrel, -K_SC[S_C], cq), sb, rep) * s1;   // 2 e^{lpn} (m/M)^-c / (1 + e)
     const double pos = fma(m, K_SC[S_INV_DMBH], K_SC[S_POS0]);
     o.pos = pos;
     int b = __double2int_rd(pos);
@@ -133,7 +138,7 @@ __device__ __forceinline__ void mass_eval(const double m, const double lm, const
     o.u = pos - (double)b;
     o.b = sb + 16u * (uint32_t)b;
     const double2 g = lds128<MASS_BYTES + MR_G * NM * 16>(o.b);
-    const double eP = fexp<false>(fma(o.u, g.y, g.x), sb);
+    const double eP = fexp<false>(fma(o.u, g.y, SHIFTED ? g.x + d : g.x), sb, rep);
     o.EP = (m < K_SC[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
     o.gy = g.y;
     o.m = m;
@@ -157,10 +162,11 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
     const double wQs = wQ * o.sgm;                         // wQ * m * logistic
     a[2 + F_T] += wQs;
     const double wPg = wP * o.gy;
-    a[2 + F_GEO] = fma(wPg, o.pos, a[2 + F_GEO]);   // wP (dP/dm) (m - 3)
+    const double geo = wPg * o.pos;                 // wP (dP/dm) (m - 3) per grid step
+    a[2 + F_GEO] += geo;
     mass_tangents<0>(o, wP, a);
-    // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c)
-    return fma(wPg * K_SC[S_INV_DMBH], o.m, fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ));
+    // weight * m dA0/dm = wP slope m + wQ (m dT/dm - c), with slope * m = gy (pos + 3 / step): pos0 = -3 / step
+    return fma(wPg, -K_SC[S_POS0], geo) + fma(wQs, K_SC[S_INV_DM], -K_SC[S_C] * wQ);
 }
 
 // Fixed-cosmology variant (the reference's `pop_model`, intensity_models.py:313-355): the sample carries source-frame
@@ -169,33 +175,30 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
 template <int SLOT, bool WA, class Mid>
 __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
                                                   const double lq, const double l1q, const double lpd,
-                                                  const uint32_t sb, ThreadAcc& A, Mid&& mid) {
+                                                  const uint32_t sb, const uint32_t rep, ThreadAcc& A, Mid&& mid) {
     double m2 = q * m1;
     double lm2 = lm1 + lq;
     const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);   // :149
-    if (!valid) {
-        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
-    }
     const double pair = lm1 + l1q;
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM], L, -lpd);   // :332 (no (1+z)^-2 Jacobian here)
     mid();
     if (valid && lin - A.m > RESCALE_GAP) {
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb);
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb, rep);
         A.a[0] *= s;
         A.a[1] *= s * s;
 #pragma unroll
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
     }
-    const double E = valid ? fexp<true>(lin - A.m, sb) : 0.0;
+    const double d = valid ? lin - A.m : 0.0;     // e^d is folded into the two exponentials of the mass function at m1
     A.nvalid += valid ? 1 : 0;
-    const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb);
+    const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb, rep);
     const double sr = frcp(1.0 + r);
     MassEval M1, M2;
-    mass_eval<SLOT>(m1, lm1, sb, M1);
-    mass_eval<SLOT>(m2, lm2, sb, M2);
+    mass_eval<SLOT, true>(m1, lm1, d, sb, rep, M1);
+    mass_eval<SLOT, false>(m2, lm2, 0.0, sb, rep, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
-    const double base = sr * E;
+    const double base = valid ? sr : 0.0;
     const double p = (sum1 * sum2) * base;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
@@ -214,7 +217,7 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
 template <int SLOT, bool WA, class Mid>
 __device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
-                                            const uint32_t sb, ThreadAcc& A, Mid&& mid) {
+                                            const uint32_t sb, const uint32_t rep, ThreadAcc& A, Mid&& mid) {
     // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
     // The bucket table, keyed by the top bits of x, gives a lower bound b0 of the bin.  A bucket (1/256 octave) is
     // narrower than any bin of the d_L grid (log dl_{k+1} - log dl_k >= ZSTEP = 0.0045 > log(1 + 1/256)), so the
@@ -249,37 +252,39 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double2 rdd = lds128<COS_BYTES + CR_DDL * NZ * 16>(ab);
     const double dvc = fma(t, rvc.y, rvc.x);
     const double ddl = fma(t, rdd.y, rdd.x);
-    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN) && (dvc > 0.0);   // :149; log(dVc/dz = 0) = -inf
-    if (!valid) {   // keep every intermediate finite; the sample gets exactly zero weight below
-        m1 = MREF; m2 = MREF; lm1 = LOG_MREF; lm2 = LOG_MREF;
-    }
+    // Zero weight (:149; log(dVc/dz = 0) = -inf).  Every intermediate of such a sample stays finite without any
+    // substitution: samples that can never be valid (m2_det < mbh_min, i.e. m2 < 5 at every redshift) are replaced by
+    // sentinels at upload, so here m1 >= m2 >= 5/101 and all exponents below are bounded; the weight is zeroed once.
+    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN) && (dvc > 0.0);
     const double iddl = frcp(ddl);
     // ---- everything that is linear in precomputed logs: beta log(m1+m2) + log m1 + (lam-2) log1p(z) - log pdraw
     const double pair = lm1 + l1q;                  // log(m1+m2); the -beta log(60) is in the constant
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM2], L, -lpd);
     mid();
     if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb);
+        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb, rep);
         A.a[0] *= s;
         A.a[1] *= s * s;
 #pragma unroll
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
     }
-    const double E = valid ? fexp<true>(lin - A.m, sb) : 0.0;
+    // e^{lin - shift} is not computed on its own: d is added to both exponents of the mass function at m1 (7 instead of
+    // 8 exponentials per sample; |d| <= RESCALE_GAP keeps the one-constant argument reduction at ~3e-14 relative)
+    const double d = valid ? lin - A.m : 0.0;
     A.nvalid += valid ? 1 : 0;
     // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
     const double kappa = K_SC[S_KAPPA];
-    const double r = fexp<false>(kappa * (L - K_SC[S_LOPZP]), sb);
+    const double r = fexp<false>(kappa * (L - K_SC[S_LOPZP]), sb, rep);
     const double sr = frcp(1.0 + r);
     const double sig = r * sr;
     // ---- mass function at both masses
     MassEval M1, M2;
-    mass_eval<SLOT>(m1, lm1, sb, M1);
-    mass_eval<SLOT>(m2, lm2, sb, M2);
-    const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
+    mass_eval<SLOT, true>(m1, lm1, d, sb, rep, M1);
+    mass_eval<SLOT, false>(m2, lm2, 0.0, sb, rep, M2);
+    const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;   // sum1 carries e^{lin - shift}
     // ---- the weight and its partial products
-    const double base = (sr * iddl) * E;            // everything but the masses and dVc/dz
+    const double base = valid ? sr * iddl : 0.0;    // everything but the masses and dVc/dz
     const double p0 = (sum1 * sum2) * base;         // weight / (dVc/dz)
     const double p = p0 * dvc;                      // e^{w - m}   (:381 / :388)
     const double bv = base * dvc;
@@ -362,16 +367,28 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int BLOB_BYTES = blob_doubles(WA, FIXED) * 8;   // the mode's share of the blob (bump_layout.cuh)
     double* s_blob = reinterpret_cast<double*>(smem_raw);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + BLOB_BYTES);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);   // inside the (unused) scalar block
 
-    stage_tables<BLOB_BYTES>(s_blob, mbar, g_blob);
+    stage_tables<BLOB_BYTES, NSCAL * 8>(s_blob, mbar, g_blob);
     // shared-window address of the blob, laundered so that it lives in one register for the whole kernel (the
     // compiler otherwise rematerialises it - S2R, MOV, LEA - in front of every table access)
     uint32_t sb = smem_u32(smem_raw);
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));
 
     const int lane = threadIdx.x & 31;
+    const uint32_t rep = (uint32_t)(lane & (EXPT_REPL - 1)) << 3;   // this lane's copy of the exp-table entries
+    // The warp index through a shuffle from lane 0: the same value, but one the compiler KNOWS to be warp-uniform.
+    // Everything derived from it (the warp's group range, the loop trip count, event boundaries) is then uniform too,
+    // the sample loop is convergent code, and ptxas keeps the theta-dependent scalars in UNIFORM registers, which FP64
+    // instructions read as a third operand for free.  With `threadIdx.x >> 5` the loop counts as divergent: every
+    // constant is then re-loaded into a vector register inside it (LDC) and turns a two-register DFMA into a
+    // three-register one (3 issue cycles instead of 2, profiles/r01_fp64_issue_microbench.txt): 17 LDC and 6 more
+    // three-register DFMAs per sample (round 2: 360 -> 345 instructions per sample).
+#ifdef BUMP_DIVERGENT_WARP_INDEX
     const int warp = blockIdx.x * STREAM_WARPS + (threadIdx.x >> 5);
+#else
+    const int warp = blockIdx.x * STREAM_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#endif
     if (warp >= wk.nwarps) return;
     // 32-bit group arithmetic (n_groups < 2^31 is checked on the host); 64-bit only to form addresses
     const int n_groups = (int)wk.n_groups, n_evt_groups = (int)wk.n_evt_groups, g_evt = (int)wk.g_evt;
@@ -421,8 +438,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32);
         auto nothing = [] {};
-        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
-        else eval_sample<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, A, nothing);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
+        else eval_sample<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
         // consumed), and the block after it is pulled towards L2 (28 lines: one per lane)
         int e_next = e, k_next = k + 1;
@@ -439,8 +456,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
             }
         };
-        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
-        else eval_sample<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, A, next_loads);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
+        else eval_sample<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);

@@ -148,6 +148,11 @@ int bump_p2p_set_timeout(bump_ctx* ctx, double seconds);
  *   which = 3: scalars [32]: log_pl_norm, log_norm, rate_log_norm, then their tangents */
 int bump_debug_tables(bump_ctx* ctx, int which, double* out, int64_t out_len);
 
+/* Accuracy probe of the streaming kernel's own scalar math, y[i] = f(x[i]) on the device (HOST arrays):
+ *   which = 0: exp, one-constant reduction (mass function, rate)   1: exp, two-constant reduction (rescaling)
+ *           2: reciprocal of a positive normal double               3: log1p on [0, 0.00453]   4: 1/(1+x) on the same */
+int bump_debug_math(bump_ctx* ctx, int which, const double* x, int64_t n, double* y);
+
 /* Timing helper for bench.py: run `iters` evaluations back to back on the context's stream with theta
  * already on the device, bracketed by CUDA events ON THAT STREAM; returns total milliseconds and, if
  * stream_ms is non-NULL, the milliseconds spent in the streaming kernel alone (events around each launch,

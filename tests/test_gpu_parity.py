@@ -363,3 +363,31 @@ def test_hubble_far_outside_the_prior_is_flagged_or_exact(hl):
         th[0] = h
         assert np.isnan(like(th).log_mu_sel), h
     like.close()
+
+
+def test_device_math(hl):
+    """The streaming kernel's own exp / reciprocal / log1p / 1/(1+x) against numpy in the ranges the kernel uses them:
+    a few ulp (the kernel's arithmetic is sized for 1e-10 on sums of 6e7 terms; these are 1e-15 - 1e-14)."""
+    import ctypes as C
+    from bumpcosmology_b200 import _lib
+    from bumpcosmology_b200.catalogs import make_catalog
+    like = hl(*make_catalog("tiny").as_args())
+    rng = np.random.default_rng(2)
+
+    def probe(which, x):
+        y = np.empty_like(x)
+        _lib.check(like.lib.bump_debug_math(like._ctx, which, _lib.as_dp(x), x.shape[0], _lib.as_dp(y)))
+        return y
+
+    x = np.concatenate([rng.uniform(-60, 60, 200_000), rng.uniform(-300, 260, 100_000), rng.uniform(-1e-3, 1e-3, 1000)])
+    rel = np.abs(probe(0, x) / np.exp(x) - 1)
+    assert np.max(rel / np.maximum(1.0, np.abs(x))) < 4e-16, float(np.max(rel))      # |x| 1.1e-16 + polynomial
+    xw = np.concatenate([rng.uniform(-700, 700, 200_000), [0.0, -0.0, 1e-300, 709.0, -708.0]])
+    assert np.max(np.abs(probe(1, xw) / np.exp(xw) - 1)) < 1.5e-15
+    assert np.all(probe(1, np.array([-800.0, -1e4, -9e4])) < 1e-300)                 # saturates: callers treat it as zero
+    xr = np.exp(rng.uniform(np.log(1e-200), np.log(1e200), 300_000))
+    assert np.max(np.abs(probe(2, xr) * xr - 1)) < 5e-16
+    xs = np.concatenate([rng.uniform(0, 0.00453, 200_000), [0.0, 0.00453]])
+    assert np.max(np.abs(probe(3, xs) - np.log1p(xs))) < 1e-17 + 2.3e-16 * 0.00453
+    assert np.max(np.abs(probe(4, xs) * (1 + xs) - 1)) < 4e-16
+    like.close()

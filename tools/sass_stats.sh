@@ -2,7 +2,7 @@
 # Static SASS statistics of stream_kernel<false,false,0> in a built library (proxy for the dynamic mix while off-GPU).
 #   tools/sass_stats.sh path/to/lib.so [top_n]
 lib=$1
-cuobjdump -sass -fun '_ZN4bump13stream_kernelILb0ELb0ELi0EEEvNS_7ColumnsENS_4WorkEPKiPKdPd' "$lib" > /tmp/sass_$$.txt 2>/dev/null
+cuobjdump -sass -fun '_ZN4bump13stream_kernelILb0ELb0ELi0EEEvNS_7ColumnsENS_4WorkEPKiPKdPdPy' "$lib" > /tmp/sass_$$.txt 2>/dev/null
 tot=$(grep -cE "^\s+/\*[0-9a-f]{4}\*/" /tmp/sass_$$.txt)
 fp=$(grep -cE "^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P[0-9T]+\s+)?(DFMA|DMUL|DADD|DSETP|DMNMX)" /tmp/sass_$$.txt)
 echo "total $tot fp64 $fp other $((tot-fp))"
