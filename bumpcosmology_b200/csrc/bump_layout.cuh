@@ -47,11 +47,13 @@ constexpr int SRCH_DOUBLES = SRCH_N / 4;
 // EXPT_REPL times in a row and lane l reads copy (l mod EXPT_REPL): the 32 lanes of a lookup at random j then spread
 // over the banks by construction (EXPT_REPL = 16: each of the 16 64-bit bank pairs serves exactly two lanes = the
 // minimum of 2 wavefronts; one copy of a 2048-entry table: ~6).  A shorter table needs a longer polynomial.
+// Measured on B200 (quarter-size O5, ns per sample): 2048 x 1: 0.0200, 1024 x 4: 0.0195, 256 x 16: 0.0183 although the
+// last needs one more FP64 instruction per exp - the kernel is bound by shared-memory wavefronts, not by issue slots.
 #ifndef BUMP_EXPT_LOG2
-#define BUMP_EXPT_LOG2 11
+#define BUMP_EXPT_LOG2 8
 #endif
 #ifndef BUMP_EXPT_REPL_LOG2
-#define BUMP_EXPT_REPL_LOG2 0
+#define BUMP_EXPT_REPL_LOG2 4
 #endif
 constexpr int NEXPT = 1 << BUMP_EXPT_LOG2;
 constexpr int EXPT_REPL = 1 << BUMP_EXPT_REPL_LOG2;

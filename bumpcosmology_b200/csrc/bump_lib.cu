@@ -911,10 +911,30 @@ int bump_debug_timeline(bump_ctx* c, const double* theta, double* out_us, int64_
     memcpy(c->h_theta, theta, sizeof(double) * nth);
     CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    {
+    if (c->flags & BUMP_FLAG_NO_GRAPH) {
         SlotGuard chain;
         if (int r = chain.begin(c, c->stream)) return r;
         if (int r = launch_eval(c, c->d_theta, c->d_out, c->stream, nullptr, nullptr, c->d_timeline)) return r;
+    } else {   // as one graph, like a normal evaluation: the gaps between the kernels are those of a graph replay
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int r = launch_eval(c, c->d_theta, c->d_out, c->stream, nullptr, nullptr, c->d_timeline);
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (r) {
+            if (g) cudaGraphDestroy(g);
+            return r;
+        }
+        CK(e);
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphDestroy(g));
+        {
+            SlotGuard chain;
+            if (int r2 = chain.begin(c, c->stream)) return r2;
+            CK(cudaGraphLaunch(ge, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGraphExecDestroy(ge));
     }
     CK(cudaMemcpyAsync(got, c->d_timeline, sizeof(got), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -22,6 +22,13 @@ from . import inputs, priors
 
 NMCMC, NCHAIN, RANDOM_SEED = 1000, 4, 1652819403   # run_cosmo_fit.py:17-19
 
+# What the reference's trace holds besides the 15 sample sites: every numpyro.deterministic of pop_cosmo_model
+# (intensity_models.py:288,294,301,394,399,401,403-406).  Downstream scripts read them by these names
+# (e.g. dNdm_fitted.py:15 uses trace.posterior.mdNdmdVdt_fixed_qz).
+REFERENCE_DETERMINISTICS = ("mbhmax", "fpl", "kappa", "neff_sel", "R", "neff", "mdNdmdVdt_fixed_qz",
+                            "dNdqdVdt_fixed_mz", "dNdVdt_fixed_mq", "hz")
+_CURVES = ("neff", "mdNdmdVdt_fixed_qz", "dNdqdVdt_fixed_mz", "dNdVdt_fixed_mq", "hz")
+
 
 def read_table(path, key="samples"):
     """A table of named columns as {name: 1-D array}.  `.h5` / `.hdf5` are read like the reference does
@@ -47,8 +54,10 @@ def read_table(path, key="samples"):
 
 
 def fit(pe, sel, num_warmup=NMCMC, num_samples=NMCMC, num_chains=NCHAIN, seed=RANDOM_SEED, device=0, cosmo=None,
-        native=True):
-    """Tables -> trace dict.  `pe`, `sel`: mappings of columns (pandas DataFrames work)."""
+        native=True, deterministics=True):
+    """Tables -> trace dict.  `pe`, `sel`: mappings of columns (pandas DataFrames work).  The trace holds the 15 sample
+    sites (`posterior`) and, as `det_<name>`, every deterministic the reference's model registers
+    (REFERENCE_DETERMINISTICS) plus the two factors."""
     from . import intensity_models as im, nuts
     args = inputs.model_arguments(pe, sel, cosmo)
     models = [im.pop_cosmo_model(*args, device=device) for _ in range(num_chains)]   # one context per chain
@@ -56,29 +65,60 @@ def fit(pe, sel, num_warmup=NMCMC, num_samples=NMCMC, num_chains=NCHAIN, seed=RA
         t0 = time.perf_counter()
         r = nuts.run_mcmc(models, num_warmup, num_samples, num_chains, seed=seed, native=native)
         wall = time.perf_counter() - t0
+        # The vector-valued deterministics (per-event neff :401, the three 128-point rate curves :403-405, hz :406) are
+        # not carried through the sampler: one more evaluation per kept draw recomputes them from the draw (the
+        # PISN table and the cosmology come from the device's own tables for that theta).
+        t0 = time.perf_counter()
+        curves = posterior_deterministics(models[0], r["x"]) if deterministics else {}
+        post_s = time.perf_counter() - t0
     finally:
         for m in models:
             m.close()
     trace = {"site_names": np.array(priors.SITE_NAMES), "posterior": r["x"],                      # [chain, draw, site]
-             "ess_bulk": r["ess_bulk"], "rhat": r["rhat"], "wall_s": wall,
+             "ess_bulk": r["ess_bulk"], "rhat": r["rhat"], "wall_s": wall, "deterministics_s": post_s,
              "warmup_s": r["warmup_s"], "sampling_s": r["sampling_s"], "n_leapfrog": r["n_leapfrog_total"],
              "nobs": args[0].shape[0], "nsamp": args[0].shape[1], "nsel": len(args[4])}
     for k in r["chains"][0]["stats"]:
         trace["stat_" + k] = np.stack([np.asarray(c["stats"][k]) for c in r["chains"]])
     for k in r["chains"][0]["deterministic"]:                                                      # :288-301,394-401
         trace["det_" + k] = np.stack([np.asarray(c["deterministic"][k]) for c in r["chains"]])
+    for k, v in curves.items():
+        trace["det_" + k] = v
     return trace
+
+
+def posterior_deterministics(model, x):
+    """x: [chain, draw, 15] constrained draws -> {name: [chain, draw, len]} for the reference's vector-valued
+    deterministics: neff [nobs] (intensity_models.py:401), mdNdmdVdt_fixed_qz, dNdqdVdt_fixed_mz, dNdVdt_fixed_mq
+    [128] (:403-405) and hz [128] (:406)."""
+    nc, nd = x.shape[:2]
+    out = {}
+    for c in range(nc):
+        for d in range(nd):
+            ev = model.evaluate(x[c, d], diagnostics=True)
+            for k in _CURVES:
+                v = np.asarray(ev[k], dtype=np.float64)
+                if k not in out:
+                    out[k] = np.empty((nc, nd) + v.shape)
+                out[k][c, d] = v
+    return out
+
+
+def posterior_variables(trace):
+    """{variable name: array [chain, draw, ...]} under the reference's names: what `az.from_numpyro(mcmc)` exposes as
+    `trace.posterior` for the reference (run_cosmo_fit.py:51): sample sites + deterministics."""
+    post = {str(n): trace["posterior"][:, :, i] for i, n in enumerate(trace["site_names"])}
+    for k, v in trace.items():
+        if k.startswith("det_"):
+            post[k[4:]] = v
+    return post
 
 
 def to_inference_data(trace):
     """arviz.InferenceData with the reference's variable names (run_cosmo_fit.py:51), if arviz is installed."""
     import arviz as az
-    post = {n: trace["posterior"][:, :, i] for i, n in enumerate(trace["site_names"])}
-    for k, v in trace.items():
-        if k.startswith("det_"):
-            post[k[4:]] = v
     stats = {k[5:]: v for k, v in trace.items() if k.startswith("stat_")}
-    return az.from_dict(posterior=post, sample_stats=stats)
+    return az.from_dict(posterior=posterior_variables(trace), sample_stats=stats)
 
 
 def main(argv=None):

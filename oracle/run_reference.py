@@ -95,6 +95,46 @@ def run_pop_cosmo_model(sites, data, R_unit=0.0, grad=True):
     return out
 
 
+ALL_SITES = SAMPLE_SITES + ("R_unit",)   # the 15 sample sites of pop_cosmo_model in the package's order
+
+
+def run_potential(u, data):
+    """The potential energy numpyro's NUTS integrates for the reference model, U(u) = -[sum_sites log_prob(x_i(u_i)) +
+    sum_sites log|dx_i/du_i| + loglike + selfactor], and dU/du, at the unconstrained point `u` (15 numbers, ALL_SITES
+    order).  The distributions and their parameters are whatever the reference's own mass_parameters /
+    redshift_parameters / cosmo_parameters / pop_cosmo_model pass to `numpyro.sample` (intensity_models.py:281-311,398):
+    a first, discarded pass records them; densities and transforms are numpyro's, restated in refshim."""
+    im = load_reference()
+    import numpyro  # the shim
+
+    # pass 1: which distribution does each site have?  (values are placeholders inside every support)
+    probe = {k: torch.tensor(v, dtype=torch.float64) for k, v in dict(
+        h=0.7, Om=0.3, w=-1.0, a=2.0, b=1.0, c=4.0, mpisn=35.0, dmbhmax=5.0, sigma=2.0, beta=0.0, log_fpl=-2.0,
+        lam=2.7, dkappa=2.9, zp=1.9, R_unit=0.0).items()}
+    with numpyro.Recorder(probe) as rec0:
+        im.pop_cosmo_model(*data)
+    dists = rec0.priors
+    assert set(dists) == set(ALL_SITES), sorted(dists)
+    # pass 2: x(u), the prior terms and the factors as one differentiable expression of u
+    uu = torch.tensor(np.asarray(u, dtype=np.float64), dtype=torch.float64, requires_grad=True)
+    vals, lp, lj = {}, 0.0, 0.0
+    for i, name in enumerate(ALL_SITES):
+        x, logj = dists[name].unconstrain_transform(uu[i])
+        vals[name] = x
+        lp = lp + dists[name].log_prob(x)
+        lj = lj + logj
+    with numpyro.Recorder(vals) as rec:
+        im.pop_cosmo_model(*data)
+    prior_part = -(lp + lj)
+    U = prior_part - rec.factors["loglike"] - rec.factors["selfactor"]
+    gU, = torch.autograd.grad(U, uu, retain_graph=True)
+    gP, = torch.autograd.grad(prior_part, uu)
+    return {"U": float(U), "grad": gU.numpy().copy(), "prior_U": float(prior_part), "prior_grad": gP.numpy().copy(),
+            "x": np.array([float(vals[k]) for k in ALL_SITES]), "loglike": float(rec.factors["loglike"]),
+            "selfactor": float(rec.factors["selfactor"]), "R": float(rec.deterministic["R"]),
+            "distributions": {k: repr(dists[k]) for k in ALL_SITES}}
+
+
 FIXED_SITES = ("a", "b", "c", "mpisn", "dmbhmax", "sigma", "beta", "log_fpl", "lam", "dkappa", "zp")
 
 

@@ -70,6 +70,20 @@ def test_fit_driver_end_to_end_from_tables(tmp_path):
     assert np.allclose(z["det_mbhmax"], x[:, :, names.index("mpisn")] + x[:, :, names.index("dmbhmax")])
     assert np.allclose(z["det_fpl"], np.exp(x[:, :, names.index("log_fpl")]))
     assert 0.5 < trace["stat_accept"].mean() <= 1.0
+    # the trace is a drop-in for the reference's trace_cosmo.nc: every sample site and every numpyro.deterministic of
+    # pop_cosmo_model (intensity_models.py:282-309,288,294,301,394,398-406) under the reference's name and shape
+    post = run_cosmo_fit.posterior_variables(trace)
+    reference_names = set(priors.SITE_NAMES) | set(run_cosmo_fit.REFERENCE_DETERMINISTICS)
+    assert reference_names <= set(post), reference_names - set(post)
+    nobs = int(trace["nobs"])
+    assert post["neff"].shape == (2, 120, nobs) and np.all(post["neff"] > 0)
+    for k in ("mdNdmdVdt_fixed_qz", "dNdqdVdt_fixed_mz", "dNdVdt_fixed_mq", "hz"):
+        assert post[k].shape == (2, 120, 128) and np.all(np.isfinite(post[k])), k
+    assert np.allclose(post["neff"].min(axis=2), trace["det_neff_min"], rtol=1e-12)   # the same draws, re-evaluated
+    h, om, w = (x[:, :, names.index(k)] for k in ("h", "Om", "w"))
+    assert np.allclose(post["hz"][:, :, 0], h) and np.all(np.diff(post["hz"], axis=2) > 0)   # hz(z=0) = h (:406)
+    # dNdVdt_fixed_mq at z = 0 is mref * R * exp(log_dN(mref, qref, zref)) = mref * R * exp(0 + ... ) (:404-405)
+    assert np.all(post["dNdVdt_fixed_mq"][:, :, 0] > 0)
 
 
 def test_fixed_cosmology_potential_gradient_and_fit_driver(tmp_path):
