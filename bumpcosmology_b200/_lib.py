@@ -53,6 +53,8 @@ SIGNATURES = {
     "bump_ctx_flags": (C.c_int, [C.c_void_p]),
     "bump_nuts_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, C.c_int, _dp, _dp,
                                   _dp, _dp, _dp, _dp, _dp]),
+    "bump_nuts_potential": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "bump_nuts_prior_terms": (C.c_int, [_dp, _dp, _dp, _dp]),
     "bump_nuts_chain_cb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                      C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp]),
 }

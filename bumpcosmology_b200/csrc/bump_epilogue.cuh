@@ -237,7 +237,8 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
                 double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
                 double* __restrict__ partial, double* __restrict__ out_header, const Peers* __restrict__ peers,
                 unsigned long long* __restrict__ exchange_state, unsigned long long* __restrict__ tl) {
-    __shared__ double red[(EPI_THREADS / 32) * (NACC + 3)];
+    __shared__ double red[32 + (EPI_THREADS / 32) * 32];
+    static_assert(32 + (EPI_THREADS / 32) * 32 >= (EPI_THREADS / 32) * (NACC + 3), "block sums fit");
     __shared__ double s_max;
     __shared__ bool is_last;
     const int tid = threadIdx.x;
@@ -353,46 +354,74 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         return;
     }
     __threadfence();
-    if (tid < NFEAT + 3) {
+    {   // column k of the slots, summed by 8 threads (blocks p, p + 8, ...) and then over p in a fixed order
+        const int k = tid & 31, p = tid >> 5;
+        static_assert(NFEAT + 3 <= 32 && EPI_THREADS == 256, "8 x 32 threads cover the slot columns");
         double s = 0.0;
-        for (int b = 0; b < nb_evt; ++b) s += __ldcg(slots + (size_t)b * EPI_SLOT + tid);
-        red[tid] = s;
+        if (k < NFEAT + 3)
+            for (int b = p; b < nb_evt; b += EPI_THREADS / 32) s += __ldcg(slots + (size_t)b * EPI_SLOT + k);
+        __syncthreads();   // `red` was last used by the block sums above
+        red[32 + p * 32 + k] = s;
+        __syncthreads();
+        if (tid < NFEAT + 3) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < EPI_THREADS / 32; ++q) t += red[32 + q * 32 + tid];
+            red[tid] = t;
+        }
     }
     __syncthreads();
-    if (tid < P_SCAL0) {
-        const double* ss = slots + (size_t)nb_evt * EPI_SLOT;
+    // this rank's partial: to global memory (host-driven / NCCL exchanges read it there) and to shared memory, from
+    // which one thread finalizes - its ~250 dependent operations then run on 30-cycle shared-memory loads instead of
+    // L2 round trips (the serial tail was half of the epilogue's time at GWTC-3 size)
+    __shared__ double s_part[P2P_MAX_RANKS * PARTIAL_LEN];
+    __shared__ double s_out[OUT_HEADER];
+    if (tid < P_SCAL0 + NSCAL) {
         double v = 0.0;
-        if (tid == P_LLSUM) v = red[0];
-        else if (tid == P_NOBS) v = (double)nobs;
-        else if (tid >= P_FSUM0 && tid < P_FSUM0 + NFEAT) v = red[3 + tid - P_FSUM0];
-        else if (tid == P_NVALID_EVT) v = red[1];
-        else if (tid == P_NDEAD_EVT) v = red[2];
-        else if (tid == P_SEL_M) v = __ldcg(ss);
-        else if (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) v = __ldcg(ss + 1 + tid - P_SEL_ACC0);
-        else if (tid == P_NVALID_SEL) v = __ldcg(ss + 1 + NACC);
-        else if (tid == P_NSEL) v = nsel;
+        if (tid < P_SCAL0) {
+            const double* ss = slots + (size_t)nb_evt * EPI_SLOT;
+            if (tid == P_LLSUM) v = red[0];
+            else if (tid == P_NOBS) v = (double)nobs;
+            else if (tid >= P_FSUM0 && tid < P_FSUM0 + NFEAT) v = red[3 + tid - P_FSUM0];
+            else if (tid == P_NVALID_EVT) v = red[1];
+            else if (tid == P_NDEAD_EVT) v = red[2];
+            else if (tid == P_SEL_M) v = __ldcg(ss);
+            else if (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) v = __ldcg(ss + 1 + tid - P_SEL_ACC0);
+            else if (tid == P_NVALID_SEL) v = __ldcg(ss + 1 + NACC);
+            else if (tid == P_NSEL) v = nsel;
+        } else {
+            v = __ldcg(blob + OFF_SCAL + tid - P_SCAL0);
+        }
         partial[tid] = v;
-    } else if (tid < P_SCAL0 + NSCAL) {
-        partial[tid] = blob[OFF_SCAL + tid - P_SCAL0];
+        s_part[tid] = v;
     }
+    static_assert(P_SCAL0 + NSCAL == PARTIAL_LEN && PARTIAL_LEN <= EPI_THREADS, "one thread per entry of the partial");
     if (tid == 0) *ticket = 0u;
     if (out_header) {
-        __threadfence();
-        __syncthreads();
+        int nparts = 1;
+        double status = STATUS_OK;
         if (peers) {   // multi-rank, fused exchange over peer memory
-            const double status = p2p_exchange(*peers, partial, exchange_state);
-            if (tid == 0) {
-                if (status == STATUS_OK) {
-                    const int par = (int)(exchange_state[0] & 1ull);
-                    finalize_merge(&peers->box[peers->rank]->mail[par][0][0], peers->nranks, out_header);
-                } else {   // the exchange failed on every rank (see p2p_exchange): no result, and say so
-                    for (int k = 0; k < OUT_HEADER; ++k) out_header[k] = (k < OUT_NVALID_EVT) ? NAN : 0.0;
-                    out_header[OUT_STATUS] = status;
-                }
+            __threadfence();
+            __syncthreads();
+            status = p2p_exchange(*peers, s_part, exchange_state);   // pushes the shared-memory copy to every peer
+            if (status == STATUS_OK) {
+                nparts = peers->nranks;
+                const int par = (int)(exchange_state[0] & 1ull);
+                const double* mail = &peers->box[peers->rank]->mail[par][0][0];
+                for (int k = tid; k < nparts * PARTIAL_LEN; k += EPI_THREADS) s_part[k] = __ldcg(mail + k);
             }
-        } else if (tid == 0) {
-            finalize_merge(partial, 1, out_header);
         }
+        __syncthreads();
+        if (tid == 0) {
+            if (status == STATUS_OK) {
+                finalize_merge(s_part, nparts, s_out);
+            } else {   // the exchange failed on every rank (see p2p_exchange): no result, and say so
+                for (int k = 0; k < OUT_HEADER; ++k) s_out[k] = (k < OUT_NVALID_EVT) ? NAN : 0.0;
+                s_out[OUT_STATUS] = status;
+            }
+        }
+        __syncthreads();
+        if (tid < OUT_HEADER) out_header[tid] = s_out[tid];
     }
     timeline_end(tl, TL_EPILOGUE);
 }

@@ -550,6 +550,29 @@ int bump_nuts_chain_cb(bump_potential_cb f, void* user, int dim, int num_warmup,
                      out_stats, nullptr, out_info, out_minv);
 }
 
+int bump_nuts_prior_terms(const double* u, double* x, double* prior_u, double* prior_grad) {
+    if (!u || !x || !prior_u || !prior_grad) return bump_set_error(BUMP_E_INVALID, "NUTS: null argument");
+    double total = 0.0;
+    for (int i = 0; i < NSITES; ++i) {
+        double dx, dlj, glp;
+        total += site_terms(sites()[i], u[i], x[i], dx, dlj, glp);
+        prior_grad[i] = -(glp * dx + dlj);
+    }
+    *prior_u = -total;
+    return BUMP_OK;
+}
+
+int bump_nuts_potential(bump_ctx* ctx, const double* u, double* U, double* grad, double* rec) {
+    if (!ctx || !u || !U || !grad) return bump_set_error(BUMP_E_INVALID, "NUTS: null argument");
+    if (bump_ctx_flags(ctx) & (BUMP_FLAG_WA | BUMP_FLAG_FIXED_COSMO))
+        return bump_set_error(BUMP_E_INVALID, "NUTS: the driver binds pop_cosmo_model (no w0-wa / fixed-cosmology contexts)");
+    ModelPotential p(ctx);
+    double r[NREC];
+    *U = p.eval(u, grad, r);
+    if (rec) memcpy(rec, r, sizeof(r));
+    return p.error();
+}
+
 int bump_nuts_chain(bump_ctx* ctx, int num_warmup, int num_samples, uint64_t seed, int dense_mass, double target_accept,
                     int max_tree_depth, const double* init_u, double* out_u, double* out_x, double* out_stats,
                     double* out_det, double* out_info, double* out_minv) {

@@ -47,7 +47,15 @@ constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far b
 // slot, so evaluations of up to NSLOT contexts (parallel NUTS chains on a small catalog) overlap on one device.
 constexpr int NSLOT = 4;
 __constant__ double K_SC4[NSLOT][NSCAL];
+#ifdef BUMP_SCALARS_IN_CONSTANT_BANK
 #define K_SC K_SC4[SLOT]   // inside templates with an `int SLOT` parameter
+#define USC_PARAM
+#define USC_ARG
+#else
+#define K_SC usc           // warp-uniform copies of the blob's scalars, made at kernel start (see stream_kernel)
+#define USC_PARAM const double (&usc)[NSCAL],
+#define USC_ARG usc,
+#endif
 
 // ---- TMA bulk copy (global -> shared) of the table blob, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,7 +130,7 @@ constexpr int SRCH_BYTES = OFF_SRCH * 8;
 // `sb` = shared-window address of the table blob.  SHIFTED: both exponents carry the extra term `d` (the sample's
 // lin - shift for the evaluation at m1, see eval_sample), i.e. the result is e^d (EP + EQ) at no extra exponential.
 template <int SLOT, bool SHIFTED>
-__device__ __forceinline__ void mass_eval(const double m, const double lm, const double d, const uint32_t sb,
+__device__ __forceinline__ void mass_eval(USC_PARAM const double m, const double lm, const double d, const uint32_t sb,
                                           const uint32_t rep, MassEval& o) {
     // -(m - M)/(0.05 M) = 20 - m/(0.05 M): one FMA
     const double e = fexp<false>(fma(m, -K_SC[S_INV_DM], 1.0 / TURNON_WIDTH), sb, rep);
@@ -155,7 +163,7 @@ __device__ __forceinline__ void mass_tangents(const MassEval& o, const double wP
 }
 
 template <int SLOT>
-__device__ __forceinline__ double mass_features(const MassEval& o, const double wp, double* __restrict__ a) {
+__device__ __forceinline__ double mass_features(USC_PARAM const MassEval& o, const double wp, double* __restrict__ a) {
     const double wQ = wp * o.EQ, wP = wp * o.EP;
     a[2 + F_SQ] += wQ;
     a[2 + F_C] = fma(wQ, o.lrel, a[2 + F_C]);
@@ -173,7 +181,7 @@ __device__ __forceinline__ double mass_features(const MassEval& o, const double 
 // (m1, q) and log1p(z) directly, `lpd` = log pdraw - log dVdzdt(z) was folded at upload, and there is no d_L
 // inversion, no Jacobian and no cosmological gradient.
 template <int SLOT, bool WA, class Mid>
-__device__ __forceinline__ void eval_sample_fixed(const double L, double m1, const double q, double lm1,
+__device__ __forceinline__ void eval_sample_fixed(USC_PARAM const double L, double m1, const double q, double lm1,
                                                   const double lq, const double l1q, const double lpd,
                                                   const uint32_t sb, const uint32_t rep, ThreadAcc& A, Mid&& mid) {
     double m2 = q * m1;
@@ -195,15 +203,15 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
     const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb, rep);
     const double sr = frcp(1.0 + r);
     MassEval M1, M2;
-    mass_eval<SLOT, true>(m1, lm1, d, sb, rep, M1);
-    mass_eval<SLOT, false>(m2, lm2, 0.0, sb, rep, M2);
+    mass_eval<SLOT, true>(USC_ARG m1, lm1, d, sb, rep, M1);
+    mass_eval<SLOT, false>(USC_ARG m2, lm2, 0.0, sb, rep, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     const double base = valid ? sr : 0.0;
     const double p = (sum1 * sum2) * base;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    mass_features<SLOT>(M1, sum2 * base, A.a);
-    mass_features<SLOT>(M2, sum1 * base, A.a);
+    mass_features<SLOT>(USC_ARG M1, sum2 * base, A.a);
+    mass_features<SLOT>(USC_ARG M2, sum1 * base, A.a);
     const double psig = p * (r * sr);
     A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
@@ -215,7 +223,7 @@ __device__ __forceinline__ void eval_sample_fixed(const double L, double m1, con
 // issuing them earlier makes the first use of THIS sample's inputs wait on a scoreboard slot shared with the fresh
 // loads, i.e. on a full L2 round trip).
 template <int SLOT, bool WA, class Mid>
-__device__ __forceinline__ void eval_sample(const double x, const double m1d, const double q, const double lm,
+__device__ __forceinline__ void eval_sample(USC_PARAM const double x, const double m1d, const double q, const double lm,
                                             const double lq, const double l1q, const double lpd,
                                             const uint32_t sb, const uint32_t rep, ThreadAcc& A, Mid&& mid) {
     // ---- z_of_dL: b = clip(searchsorted(dl, x, side='right'), 1, n-1) - 1   (:272-273, jnp.interp)
@@ -280,8 +288,8 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double sig = r * sr;
     // ---- mass function at both masses
     MassEval M1, M2;
-    mass_eval<SLOT, true>(m1, lm1, d, sb, rep, M1);
-    mass_eval<SLOT, false>(m2, lm2, 0.0, sb, rep, M2);
+    mass_eval<SLOT, true>(USC_ARG m1, lm1, d, sb, rep, M1);
+    mass_eval<SLOT, false>(USC_ARG m2, lm2, 0.0, sb, rep, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;   // sum1 carries e^{lin - shift}
     // ---- the weight and its partial products
     const double base = valid ? sr * iddl : 0.0;    // everything but the masses and dVc/dz
@@ -290,7 +298,7 @@ __device__ __forceinline__ void eval_sample(const double x, const double m1d, co
     const double bv = base * dvc;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    const double md = mass_features<SLOT>(M1, sum2 * bv, A.a) + mass_features<SLOT>(M2, sum1 * bv, A.a);
+    const double md = mass_features<SLOT>(USC_ARG M1, sum2 * bv, A.a) + mass_features<SLOT>(USC_ARG M2, sum1 * bv, A.a);
     // ---- d w / d t at fixed tables (times p), then the cosmological tangents
     const double lt = zeps * u1;                    // d log1p(z) / dt
     const double psig = p * sig;
@@ -369,7 +377,29 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     double* s_blob = reinterpret_cast<double*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);   // inside the (unused) scalar block
 
+#ifndef BUMP_SCALARS_IN_CONSTANT_BANK
+    // The theta-dependent scalars: lane l fetches scal[l] and scal[32 + l] from the blob in global memory (the loads
+    // fly while the tables are staged), and every scalar the loop needs is broadcast from its lane.  A shuffle from a
+    // fixed lane is a value the compiler knows to be warp-uniform: it goes to a UNIFORM register, which an FP64
+    // instruction reads as its third operand at no issue cost - what the constant bank offered in round 1, without the
+    // device-to-device copy into the bank before every launch (13 us of every evaluation, and the reason contexts had
+    // to share four constant-bank slots).
+    const double sc_lo = __ldcg(g_blob + OFF_SCAL + (threadIdx.x & 31));
+    const double sc_hi = __ldcg(g_blob + OFF_SCAL + 32 + (threadIdx.x & 31));
+#endif
     stage_tables<BLOB_BYTES, NSCAL * 8>(s_blob, mbar, g_blob);
+#ifndef BUMP_SCALARS_IN_CONSTANT_BANK
+    double usc[NSCAL];
+    {
+        constexpr int used[] = {S_C, S_LOG_M, S_INV_DM, S_TOP, S_INV_DMBH, S_BETA, S_LAM, S_KAPPA, S_LOPZP, S_DL_LAST,
+                                S_ZEPS, S_LAM2, S_RATE0, S_LOG_C2, S_POS0};
+#pragma unroll
+        for (int k = 0; k < NSCAL; ++k) usc[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < (int)(sizeof(used) / sizeof(int)); ++j)
+            usc[used[j]] = __shfl_sync(0xffffffffu, used[j] < 32 ? sc_lo : sc_hi, used[j] & 31);
+    }
+#endif
     // shared-window address of the blob, laundered so that it lives in one register for the whole kernel (the
     // compiler otherwise rematerialises it - S2R, MOV, LEA - in front of every table access)
     uint32_t sb = smem_u32(smem_raw);
@@ -438,8 +468,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32);
         auto nothing = [] {};
-        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
-        else eval_sample<SLOT, WA>(hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(USC_ARG hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
+        else eval_sample<SLOT, WA>(USC_ARG hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
         // consumed), and the block after it is pulled towards L2 (28 lines: one per lane)
         int e_next = e, k_next = k + 1;
@@ -456,8 +486,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
             }
         };
-        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
-        else eval_sample<SLOT, WA>(hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
+        if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(USC_ARG hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
+        else eval_sample<SLOT, WA>(USC_ARG hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
         if (!more || e_next != e) {   // event complete (for this warp): one record
             warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);
@@ -469,5 +499,7 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
 }
 
 #undef K_SC
+#undef USC_PARAM
+#undef USC_ARG
 
 }  // namespace bump

@@ -133,8 +133,59 @@ __device__ void pisn_row(const double* __restrict__ th, int i, double* __restric
 // its own shared memory, one cluster barrier, then each block adds the totals of the chunks before it.
 constexpr int COS_CHUNKS = 4;
 
-__device__ void cosmology_tables(const double* __restrict__ th, int use_wa, double* __restrict__ aux, double* sm,
-                                 const int chunk) {
+constexpr int COS_VALS = 13;        // z, dl, ddl, dvc and the 9 tangents of one knot
+constexpr int COS_EX0 = 80;         // offset of the neighbour-exchange area in the block's shared array
+constexpr int PRO_SMEM_DOUBLES = COS_EX0 + COS_VALS * PRO_THREADS;
+static_assert(PRO_SMEM_DOUBLES >= 9 * NM + 64, "the PISN rows use 9 NM + 64 doubles of the same array");
+
+// One bin of the packed cosmology tables: lo / hi = the 13 numbers of its left / right knot, own = those of knot b
+// itself (differs from lo only for the padding record NZ-1).  Formats: bump_layout.cuh.
+__device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo, const double* hi, const double* own,
+                                                   double* __restrict__ blob, const EvalConsts ec) {
+    double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
+    const int b0 = min(b, NZ - 2);
+    cos[CR_DL * NZ + b] = make_double2(lo[1], 1.0 / (hi[1] - lo[1]));
+    cos[CR_DVC * NZ + b] = make_double2(lo[3], hi[3] - lo[3]);
+    cos[CR_DDL * NZ + b] = make_double2(lo[2], hi[2] - lo[2]);
+    cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + lo[0]), b0 * ZSTEP);
+    if (ec.fixed) return;
+    // tangent tables: value order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
+    // pairs {t_b, t_{b+1} - t_b} otherwise, nothing in fixed-cosmology mode
+    const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
+    double* ctan = blob + OFF_CTAN;
+    if (ec.use_wa) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = own[4 + r];
+    } else {
+        double2* ctan2 = reinterpret_cast<double2*>(ctan);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            if (r % 3 == 2) continue;   // the wa tangents
+            ctan2[dst[r] * NZ + b] = make_double2(lo[4 + r], hi[4 + r] - lo[4 + r]);
+        }
+    }
+    // ---- bucket table of the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j, i.e.
+    // for the smallest double x0_j of the bucket: clip(#{k < NZ-1 : dl_k <= x0_j}, 1, .) - 1.  Knot b owns the
+    // buckets whose x0_j lies in [dl_b, dl_{b+1}) (the last knot up to +inf): filled without any search.
+    if (b <= NZ - 2) {
+        unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
+        auto first_bucket_at_or_above = [](const double v) -> int {   // min{j : x0_j >= v}, clamped to [0, SRCH_N]
+            if (!(v > 0.0)) return 0;
+            const int key = (__double2hiint(v) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
+            if (key < 0) return 0;
+            if (key >= SRCH_N) return SRCH_N;
+            const bool exact = __double2loint(v) == 0 && (__double2hiint(v) & ((1 << (20 - SRCH_MBITS)) - 1)) == 0;
+            return exact ? key : key + 1;
+        };
+        const int j0 = (b == 0) ? 0 : first_bucket_at_or_above(lo[1]);
+        const int j1 = (b == NZ - 2) ? SRCH_N : first_bucket_at_or_above(hi[1]);
+        for (int j = j0; j < j1; ++j) srch[j] = (unsigned short)(j == 0 ? 0 : b);
+    }
+}
+
+__device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts ec, double* __restrict__ aux,
+                                 double* __restrict__ blob, double* sm, const int chunk) {
+    const int use_wa = ec.use_wa;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     typedef Dual<3> D;
@@ -203,36 +254,50 @@ __device__ void cosmology_tables(const double* __restrict__ th, int use_wa, doub
 #pragma unroll
         for (int c = 0; c < 4; ++c) sm[64 + c] = p4[c];
     }
-    cluster.sync();   // no block may exit (and release its shared memory) while a peer still reads its total
+    cluster.sync();   // the totals have been read: their slots may be reused, and nobody exits before this point
     double base[4] = {sm[64], sm[65], sm[66], sm[67]};
     for (int ww = 0; ww < warp; ++ww) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) base[c] += sm[ww * 4 + c];
     }
-    D C;  // exclusive prefix for this thread's first knot
+    static_assert(PER == 1, "one knot per thread: the packing below exchanges one value set with the right neighbour");
+    D C;  // exclusive prefix for this thread's knot
     C.v = base[0] + sc[0] - tot.v;
 #pragma unroll
     for (int c = 0; c < 3; ++c) C.d[c] = base[c + 1] + sc[c + 1] - tot.d[c];
+    const int k = tid;
+    const double opz = 1.0 + z[0];
+    const D dc = dH * C;                                        // :231
+    const D dl = dc * opz;                                      // :232
+    const D ddl = dc + (dH * opz) * iE[0];                      // :233
+    const D dvc = (FOUR_PI * dH) * (dsquare(dc) * iE[0]);       // :235
+    // the knot's 13 numbers in aux order: z, dl, ddl, dvc, then the tangents [dl, ddl, dvc][Om, w, wa]
+    double me[COS_VALS] = {z[0], dl.v, ddl.v, dvc.v, dl.d[0], dl.d[1], dl.d[2], ddl.d[0], ddl.d[1], ddl.d[2],
+                           dvc.d[0], dvc.d[1], dvc.d[2]};
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int k = tid * PER + q;
-        const double opz = 1.0 + z[q];
-        D dc = dH * C;                                        // :231
-        D dl = dc * opz;                                      // :232
-        D ddl = dc + (dH * opz) * iE[q];                      // :233
-        D dvc = (FOUR_PI * dH) * (dsquare(dc) * iE[q]);       // :235
-        aux[AUX_ZG + k] = z[q];
-        aux[AUX_DL + k] = dl.v;
-        aux[AUX_DDL + k] = ddl.v;
-        aux[AUX_DVC + k] = dvc.v;
+    for (int r = 0; r < COS_VALS; ++r) aux[r * NZ + k] = me[r];   // raw knots (bump_debug_tables, scalars)
+    static_assert(AUX_ZG == 0 && AUX_DL == NZ && AUX_DDL == 2 * NZ && AUX_DVC == 3 * NZ && AUX_TAN == 4 * NZ,
+                  "aux order of the 13 cosmology value sets");
+    // ---- packed per-bin records, straight from the registers: bin b = [knot b, knot b+1] needs the right neighbour's
+    // numbers - the next thread's through shared memory, the next chunk's first thread's through distributed shared
+    // memory.  (Round 1 packed them in a second kernel, round 2 first in the prologue's last block: ~7 us of its tail.)
+    double* ex = sm + COS_EX0;   // [COS_VALS][PRO_THREADS]
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            aux[AUX_TAN + (0 * 3 + c) * NZ + k] = dl.d[c];
-            aux[AUX_TAN + (1 * 3 + c) * NZ + k] = ddl.d[c];
-            aux[AUX_TAN + (2 * 3 + c) * NZ + k] = dvc.d[c];
-        }
-        C = C + inc[q];
+    for (int r = 0; r < COS_VALS; ++r) ex[r * PRO_THREADS + threadIdx.x] = me[r];
+    cluster.sync();
+    double lo[COS_VALS], hi[COS_VALS];
+    const bool last_knot = (k == NZ - 1);   // record NZ-1 is padding: a copy of bin NZ-2 = [left neighbour, this knot]
+    if (!last_knot) {
+        const double* src = (threadIdx.x + 1 < PRO_THREADS) ? ex + threadIdx.x + 1
+                                                            : cluster.map_shared_rank(ex, chunk + 1);
+#pragma unroll
+        for (int r = 0; r < COS_VALS; ++r) lo[r] = me[r], hi[r] = src[r * PRO_THREADS];
+    } else {
+#pragma unroll
+        for (int r = 0; r < COS_VALS; ++r) lo[r] = ex[r * PRO_THREADS + threadIdx.x - 1], hi[r] = me[r];
     }
+    pack_cosmology_bin(k, lo, hi, me, blob, ec);
+    cluster.sync();   // no block may exit (and release its shared memory) while a peer still reads its knot
 }
 
 // ---------------------------------------------------------------- scalars
@@ -330,69 +395,17 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
     scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
 
-// ---------------------------------------------------------------- packed records (last block of the prologue)
-// One item per thread and step: NZ cosmology bins, NM mass bins, NZ - 1 knots of the d_L bucket table (the exp table
-// of the blob is theta-independent and written once at context creation).  Runs in warps 1..7 of the block while warp
-// 0 derives the scalars.  aux was written by other blocks of this launch: read through L2.
-__device__ void pack_records(const double* __restrict__ aux_, double* __restrict__ blob, const EvalConsts ec,
-                             const int t /* 0 .. nt-1 */, const int nt) {
-    const CgView aux{aux_};
-    double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
-    double* ctan = blob + OFF_CTAN;
-    for (int b = t; b < NZ; b += nt) {
-        const int b0 = min(b, NZ - 2), b1 = b0 + 1;   // record NZ-1 is padding (copy of the last bin)
-        const CgView dl = aux + AUX_DL, dvc = aux + AUX_DVC, ddl = aux + AUX_DDL;
-        const double dl0 = dl[b0], dl1 = dl[b1];
-        cos[CR_DL * NZ + b] = make_double2(dl0, 1.0 / (dl1 - dl0));
-        const double v0 = dvc[b0], d0 = ddl[b0];
-        cos[CR_DVC * NZ + b] = make_double2(v0, dvc[b1] - v0);
-        cos[CR_DDL * NZ + b] = make_double2(d0, ddl[b1] - d0);
-        cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + aux[AUX_ZG + b0]), b0 * ZSTEP);
-        // tangent tables: aux order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
-        // pairs {t_b, t_{b+1} - t_b} otherwise (bump_layout.cuh), nothing in fixed-cosmology mode
-        const int dst[9] = {CT_DL_OM, CT_DL_W, CT_DL_WA, CT_DDL_OM, CT_DDL_W, CT_DDL_WA, CT_DVC_OM, CT_DVC_W, CT_DVC_WA};
-        if (!ec.fixed) {
-            if (ec.use_wa) {
-#pragma unroll
-                for (int r = 0; r < 9; ++r) ctan[dst[r] * NZ + b] = aux[AUX_TAN + r * NZ + b];
-            } else {
-                double2* ctan2 = reinterpret_cast<double2*>(ctan);
-#pragma unroll
-                for (int r = 0; r < 9; ++r) {
-                    if (r % 3 == 2) continue;   // the wa tangents
-                    const CgView tt = aux + (AUX_TAN + r * NZ);
-                    const double t0 = tt[b0];
-                    ctan2[dst[r] * NZ + b] = make_double2(t0, tt[b1] - t0);
-                }
-            }
-        }
-        // ---- bucket table of the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j, i.e.
-        // for the smallest double x0_j of the bucket: clip(#{k < NZ-1 : dl_k <= x0_j}, 1, .) - 1.  Knot b owns the
-        // buckets whose x0_j lies in [dl_b, dl_{b+1}) (the last knot up to +inf): filled without any search.
-        if (!ec.fixed && b <= NZ - 2) {
-            unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
-            auto first_bucket_at_or_above = [](const double v) -> int {   // min{j : x0_j >= v}, clamped to [0, SRCH_N]
-                if (!(v > 0.0)) return 0;
-                const int key = (__double2hiint(v) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
-                if (key < 0) return 0;
-                if (key >= SRCH_N) return SRCH_N;
-                const bool exact = __double2loint(v) == 0 && (__double2hiint(v) & ((1 << (20 - SRCH_MBITS)) - 1)) == 0;
-                return exact ? key : key + 1;
-            };
-            const int j0 = (b == 0) ? 0 : first_bucket_at_or_above(dl0);
-            const int j1 = (b == NZ - 2) ? SRCH_N : first_bucket_at_or_above(dl1);
-            for (int j = j0; j < j1; ++j) srch[j] = (unsigned short)(j == 0 ? 0 : b);
-        }
-    }
+// ---------------------------------------------------------------- packed mass records (last block of the prologue)
+// Bin i of the mbh grid needs rows i and i + 1 of the PISN table, i.e. two different blocks: packed once all rows are
+// done, by warps 1..7 of the last block while warp 0 derives the scalars.  aux was written by other blocks: read via L2.
+__device__ void pack_mass_records(const double* __restrict__ gtab /* shared copy [6][NM] */, double* __restrict__ blob,
+                                  const int t /* 0 .. nt-1 */, const int nt) {
     double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
-    for (int item = t; item < NM; item += nt) {
-        const int b0 = min(item, NM - 2), b1 = b0 + 1;
-#pragma unroll
-        for (int r = 0; r < NMREC; ++r) {
-            const CgView g = aux + (AUX_G + r * NM);
-            const double g0 = g[b0];
-            mass[r * NM + item] = make_double2(g0, g[b1] - g0);
-        }
+    for (int item = t; item < NMREC * NM; item += nt) {
+        const int r = item / NM, i = item - r * NM;
+        const int b0 = min(i, NM - 2);
+        const double g0 = gtab[r * NM + b0];
+        mass[item] = make_double2(g0, gtab[r * NM + b0 + 1] - g0);
     }
 }
 
@@ -400,7 +413,8 @@ __device__ void pack_records(const double* __restrict__ aux_, double* __restrict
 //   blocks 0..3        : flat wCDM distance tables, 256 knots each (intensity_models.py:229-235 + utils.py:3-8); they
 //                        are one cluster and chain their cumulative trapezoid through distributed shared memory
 //   blocks 4..4+NM-1   : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
-//   the block that finishes last (ticket): packed records + d_L bucket table (warps 1..7) and the scalars
+//                        and pack their bins of the cosmology records and of the d_L bucket table themselves
+//   the block that finishes last (ticket): packed mass records (warps 1..7) and the scalars
 //                        (intensity_models.py:134-138,167-168; 7 threads of warp 0) -> the blob the streaming kernel stages
 constexpr int PRO_BLOCKS = NM + COS_CHUNKS;
 static_assert(PRO_BLOCKS % COS_CHUNKS == 0, "the grid is a whole number of clusters");
@@ -409,7 +423,7 @@ __global__ void __cluster_dims__(COS_CHUNKS, 1, 1) __launch_bounds__(PRO_THREADS
 prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
                 unsigned int* __restrict__ flags /* [0] ticket, [1] bad */, const EvalConsts ec,
                 unsigned long long* __restrict__ tl) {
-    __shared__ double sm[9 * NM + 64];
+    __shared__ double sm[PRO_SMEM_DOUBLES];
     __shared__ double th[NTHETA_MAX];
     __shared__ bool is_last;
     timeline_begin(tl, TL_PROLOGUE);
@@ -419,7 +433,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     const bool is_cos = blockIdx.x < COS_CHUNKS;    // cosmology chunks first: they are the longer chains
     const int row = (int)blockIdx.x - COS_CHUNKS;
     if (!is_cos) pisn_row(th, row, aux, sm);
-    else cosmology_tables(th, use_wa, aux, sm, blockIdx.x);
+    else cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     int bad = 0;
     __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
@@ -445,11 +459,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
     __syncthreads();
     if (threadIdx.x < 32) {
-        if (threadIdx.x < 7) {
-            double thr[NTHETA_MAX];
-            for (int k = 0; k < NTHETA_MAX; ++k) thr[k] = th[k];
-            build_scalars(thr, aux, gtab, ec, blob + OFF_SCAL, threadIdx.x);
-        }
+        if (threadIdx.x < 7) build_scalars(th, aux, gtab, ec, blob + OFF_SCAL, threadIdx.x);
         if (threadIdx.x == 0) {
             // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
             // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
@@ -464,7 +474,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
             flags[1] = 0u;
         }
     } else {
-        pack_records(aux, blob, ec, threadIdx.x - 32, PRO_THREADS - 32);
+        pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
     }
     timeline_end(tl, TL_PROLOGUE);
 }

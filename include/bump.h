@@ -188,6 +188,14 @@ int bump_plan_info(bump_ctx* ctx, int64_t* info8);
 int bump_nuts_chain(bump_ctx* ctx, int num_warmup, int num_samples, uint64_t seed, int dense_mass, double target_accept,
                     int max_tree_depth, const double* init_u, double* out_u, double* out_x, double* out_stats,
                     double* out_det, double* out_info, double* out_minv);
+/* What the driver integrates, exposed for parity tests against the reference-minted potential golden
+ * (tests/golden/potential_small.npz): the potential energy of pop_cosmo_model in unconstrained space,
+ *   U(u) = -[sum_i log prior_i(x_i(u_i)) + sum_i log|dx_i/du_i| + loglike + selfactor]   (numpyro's potential_energy)
+ * and dU/du for the 15 sites; rec[BUMP_NUTS_NDET] (may be NULL) = the deterministics of that evaluation.
+ * bump_nuts_prior_terms is the prior + Jacobian part alone (no GPU): x[15] = constrained values, *prior_u and
+ * prior_grad[15] = that part of U and of dU/du. */
+int bump_nuts_potential(bump_ctx* ctx, const double* u, double* U, double* grad, double* rec);
+int bump_nuts_prior_terms(const double* u, double* x, double* prior_u, double* prior_grad);
 /* The same sampler on an arbitrary potential U(u) with gradient (dim <= 32): the CPU-testable core. */
 typedef double (*bump_potential_cb)(void* user, const double* u, double* grad);
 int bump_nuts_chain_cb(bump_potential_cb f, void* user, int dim, int num_warmup, int num_samples, uint64_t seed,

@@ -25,10 +25,10 @@ inner = None
 for a, t in ins:
     if "BRA" in t and lo <= a <= hi:
         m2 = re.search(r"0x([0-9a-f]+)", t)
-        if m2 and lo < int(m2.group(1), 16) < a and t.startswith("@"):
+        if m2 and lo < int(m2.group(1), 16) < a and (t.startswith("@") or "BRA.U UP" in t):
             if inner is None or a - int(m2.group(1), 16) > inner[1] - inner[0]:
                 inner = (int(m2.group(1), 16), a)
-if inner:
+if inner and inner[1] - inner[0] > 0x800:
     lo, hi = inner
 # cold regions: bodies skipped by a predicated forward branch of >= 32 instructions (the accumulator rescale, the
 # warp flush at an event boundary)
