@@ -347,6 +347,8 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     // ---- last block: fixed-order sum of the slots
     __threadfence();
     __syncthreads();
+    timeline_begin(tl, TL_EPI_BLOCKS);   // (its minimum is meaningless: only the end of the phase is of interest)
+    timeline_end(tl, TL_EPI_BLOCKS);
     if (tid == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) {
@@ -354,6 +356,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         return;
     }
     __threadfence();
+    timeline_begin(tl, TL_EPI_LAST);
     {   // column k of the slots, summed by 8 threads (blocks p, p + 8, ...) and then over p in a fixed order
         const int k = tid & 31, p = tid >> 5;
         static_assert(NFEAT + 3 <= 32 && EPI_THREADS == 256, "8 x 32 threads cover the slot columns");
@@ -423,6 +426,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         __syncthreads();
         if (tid < OUT_HEADER) out_header[tid] = s_out[tid];
     }
+    timeline_end(tl, TL_EPI_LAST);
     timeline_end(tl, TL_EPILOGUE);
 }
 

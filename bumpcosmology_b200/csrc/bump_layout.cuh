@@ -183,7 +183,14 @@ constexpr double STATUS_OK = 0.0, STATUS_EXCHANGE_TIMEOUT = 1.0, STATUS_EXCHANGE
 
 // ---- optional per-kernel timeline (bump_debug_timeline): first block start / last block end of every kernel of one
 // evaluation on the GPU's global nanosecond timer.  tl == nullptr (always, on the normal path) costs one predicate.
-enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE, TL_N };
+enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE,
+                    TL_PRO_ROWS,      // prologue: the 256 PISN-row blocks (start of the first .. end of the last)
+                    TL_PRO_COSMO,     // prologue: the 4 cosmology blocks incl. their packing
+                    TL_PRO_LAST,      // prologue: the last block's tail (mass records, scalars)
+                    TL_STREAM_STAGED, // streaming kernel: first .. last CTA past the table staging
+                    TL_EPI_BLOCKS,    // epilogue: per-event / injection phase of all blocks
+                    TL_EPI_LAST,      // epilogue: the last block's tail (slot sums, partial, exchange, finalize)
+                    TL_N };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;

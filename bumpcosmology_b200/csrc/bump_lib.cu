@@ -394,7 +394,7 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr,
                    unsigned long long* tl = nullptr) {
     prologue_kernel<<<PRO_BLOCKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 4, consts_of(c), tl);
-#ifdef BUMP_SCALARS_IN_CONSTANT_BANK
+#ifndef BUMP_SCALARS_FROM_BLOB
     CK(cudaMemcpyToSymbolAsync(K_SC4, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL,
                                sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
 #endif

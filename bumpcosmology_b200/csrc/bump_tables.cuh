@@ -141,7 +141,8 @@ static_assert(PRO_SMEM_DOUBLES >= 9 * NM + 64, "the PISN rows use 9 NM + 64 doub
 // One bin of the packed cosmology tables: lo / hi = the 13 numbers of its left / right knot, own = those of knot b
 // itself (differs from lo only for the padding record NZ-1).  Formats: bump_layout.cuh.
 __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo, const double* hi, const double* own,
-                                                   double* __restrict__ blob, const EvalConsts ec) {
+                                                   double* __restrict__ blob, const EvalConsts ec, int& j0, int& j1) {
+    j0 = j1 = 0;   // this bin's range of the d_L bucket table (empty in fixed-cosmology mode and for the padding bin)
     double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
     const int b0 = min(b, NZ - 2);
     cos[CR_DL * NZ + b] = make_double2(lo[1], 1.0 / (hi[1] - lo[1]));
@@ -166,9 +167,9 @@ __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo
     }
     // ---- bucket table of the d_L search: srch[j] = a bin index that is <= the bin of every x in bucket j, i.e.
     // for the smallest double x0_j of the bucket: clip(#{k < NZ-1 : dl_k <= x0_j}, 1, .) - 1.  Knot b owns the
-    // buckets whose x0_j lies in [dl_b, dl_{b+1}) (the last knot up to +inf): filled without any search.
+    // buckets whose x0_j lies in [dl_b, dl_{b+1}) (the last knot up to +inf): no search.  The caller fills the ranges
+    // warp-cooperatively (the first knots own hundreds of buckets each: d_L grows linearly from 0 there).
     if (b <= NZ - 2) {
-        unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
         auto first_bucket_at_or_above = [](const double v) -> int {   // min{j : x0_j >= v}, clamped to [0, SRCH_N]
             if (!(v > 0.0)) return 0;
             const int key = (__double2hiint(v) >> (20 - SRCH_MBITS)) - (SRCH_EXP_LO << SRCH_MBITS);
@@ -177,9 +178,8 @@ __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo
             const bool exact = __double2loint(v) == 0 && (__double2hiint(v) & ((1 << (20 - SRCH_MBITS)) - 1)) == 0;
             return exact ? key : key + 1;
         };
-        const int j0 = (b == 0) ? 0 : first_bucket_at_or_above(lo[1]);
-        const int j1 = (b == NZ - 2) ? SRCH_N : first_bucket_at_or_above(hi[1]);
-        for (int j = j0; j < j1; ++j) srch[j] = (unsigned short)(j == 0 ? 0 : b);
+        j0 = (b == 0) ? 0 : first_bucket_at_or_above(lo[1]);
+        j1 = (b == NZ - 2) ? SRCH_N : first_bucket_at_or_above(hi[1]);
     }
 }
 
@@ -296,7 +296,16 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
 #pragma unroll
         for (int r = 0; r < COS_VALS; ++r) lo[r] = ex[r * PRO_THREADS + threadIdx.x - 1], hi[r] = me[r];
     }
-    pack_cosmology_bin(k, lo, hi, me, blob, ec);
+    int j0, j1;
+    pack_cosmology_bin(k, lo, hi, me, blob, ec, j0, j1);
+    {
+        unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
+        for (int src = 0; src < 32; ++src) {   // the 32 ranges of this warp, each filled by all of its lanes
+            const int a0 = __shfl_sync(0xffffffffu, j0, src), a1 = __shfl_sync(0xffffffffu, j1, src);
+            const int bb = __shfl_sync(0xffffffffu, k, src);
+            for (int j = a0 + lane; j < a1; j += 32) srch[j] = (unsigned short)(j == 0 ? 0 : bb);
+        }
+    }
     cluster.sync();   // no block may exit (and release its shared memory) while a peer still reads its knot
 }
 
@@ -432,8 +441,10 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     __syncthreads();
     const bool is_cos = blockIdx.x < COS_CHUNKS;    // cosmology chunks first: they are the longer chains
     const int row = (int)blockIdx.x - COS_CHUNKS;
+    timeline_begin(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     if (!is_cos) pisn_row(th, row, aux, sm);
     else cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
+    timeline_end(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     int bad = 0;
     __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
@@ -455,6 +466,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
         return;
     }
     __threadfence();
+    timeline_begin(tl, TL_PRO_LAST);
     double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
     for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
     __syncthreads();
@@ -476,6 +488,8 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     } else {
         pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
     }
+    __syncthreads();
+    timeline_end(tl, TL_PRO_LAST);
     timeline_end(tl, TL_PROLOGUE);
 }
 

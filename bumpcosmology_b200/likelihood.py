@@ -199,9 +199,10 @@ class Hyperlikelihood:
         """Per-kernel timeline of one evaluation launched directly (no graph): {kernel: (start_us, end_us)} on the
         GPU's global timer, relative to the first kernel's first block."""
         th = self._set_theta(theta)
-        buf = np.empty(8)
-        _lib.check(self.lib.bump_debug_timeline(self._ctx, _lib.as_dp(th), _lib.as_dp(buf), 8))
-        names = ("prologue", "stream", "epilogue", "finalize")
+        names = ("prologue", "stream", "epilogue", "finalize", "prologue.rows", "prologue.cosmology", "prologue.last_block",
+                 "stream.staged", "epilogue.blocks", "epilogue.last_block")
+        buf = np.empty(2 * len(names))
+        _lib.check(self.lib.bump_debug_timeline(self._ctx, _lib.as_dp(th), _lib.as_dp(buf), buf.shape[0]))
         return {n: (float(buf[2 * i]), float(buf[2 * i + 1])) for i, n in enumerate(names) if buf[2 * i + 1] >= 0}
 
     def plan(self):
