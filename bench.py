@@ -550,8 +550,8 @@ def main():
                 "gwtc3_nuts": nuts_record("gwtc3_nuts", 1000, 1000, 4, local_rank, cpu_gwtc3),
                 # the standard catalog keeps ~3 % of its samples at the model's hard cut m >= 5 (intensity_models.py:
                 # 149): logL jumps as (h, Om, w) move samples across it and NUTS stalls, so
-                # this run is bounded to 4 x (150 + 150) and reported as found
-                "gwtc3": nuts_record("gwtc3", 150, 150, 4, local_rank, cpu_gwtc3),
+                # this run is bounded to 4 x (60 + 60) and reported as found
+                "gwtc3": nuts_record("gwtc3", 60, 60, 4, local_rank, cpu_gwtc3),
                 "metric": "min bulk-ESS over the 14 likelihood sites / wall seconds (warm-up included) and / "
                           "sampling seconds; rank-normalised split-chain ESS (arviz formula)"}
         except Exception as e:  # noqa: BLE001

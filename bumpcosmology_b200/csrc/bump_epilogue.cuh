@@ -18,7 +18,14 @@ constexpr int EPI_THREADS = 256;
 
 // Gradient of (logsumexp + theta-only constant) from softmax-weighted features phi (already normalised and, for
 // events, summed over n events).  g[15] in theta order; sc = scalar block of the table blob.
-__host__ __device__ inline void grad_from_features(const double* phi, const double n, const double* sc, double* g) {
+// (not inlined on the device: it runs twice in the single-thread tail of the epilogue, whose instructions come from a
+// cold instruction cache after a streaming kernel that swept L2 - code size is latency there)
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+void grad_from_features(const double* phi, const double n, const double* sc, double* g) {
     const double inv_h = sc[S_INV_H];
     const double c = sc[S_C], M = sc[S_M], kappa = sc[S_KAPPA], zp = sc[S_ZP];
     const double sq = phi[F_SQ];
@@ -218,12 +225,6 @@ __device__ __forceinline__ void epi_block_sum(double (&v)[NV], double* red) {
     }
 }
 
-// Record index of (warp w, event e): warp w's records start at rec_off[w] and are ordered by event.
-__device__ __forceinline__ size_t record_of(const Work& wk, const int* __restrict__ rec_off, const int64_t w,
-                                            const int64_t e) {
-    return (size_t)rec_off[w] + (size_t)(e - group_event(wk, w * wk.gpw));
-}
-
 // part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt)) is covered
 // by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
 //   blocks 0 .. nb_evt-1 : one thread per event -> logsumexp, Neff, normalised features; block sum -> slot[b]
@@ -247,6 +248,12 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     const int epb = EPI_THREADS / lpe;   // events per block
     const int nb_evt = (nobs + epb - 1) / epb;
     double* slot = slots + (size_t)blockIdx.x * EPI_SLOT;
+    // 32-bit group arithmetic (n_groups < 2^31 is checked on the host; 64-bit divisions are emulated and slow)
+    const int g_evt = (int)wk.g_evt, gpw = (int)wk.gpw, n_evt_groups = (int)wk.n_evt_groups, n_groups = (int)wk.n_groups;
+    auto rec_index = [&](const int w, const int e) {   // warp w's records start at rec_off[w], ordered by event
+        const int g0 = w * gpw;
+        return rec_off[w] + (e - (g0 < n_evt_groups ? g0 / g_evt : nobs));
+    };
     if ((int)blockIdx.x < nb_evt) {
         // ---- events
         double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
@@ -258,9 +265,9 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
 #pragma unroll
         for (int k = 0; k < NACC; ++k) a[k] = 0.0;
         if (e < nobs) {
-            const int64_t w0 = (e * wk.g_evt) / wk.gpw, w1 = ((e + 1) * wk.g_evt - 1) / wk.gpw;
-            for (int64_t w = w0 + sub; w <= w1; w += lpe) {
-                const double* p = part + record_of(wk, rec_off, w, e) * PART_STRIDE;
+            const int w0 = (e * g_evt) / gpw, w1 = ((e + 1) * g_evt - 1) / gpw;
+            for (int w = w0 + sub; w <= w1; w += lpe) {   // one record per lane unless the event spans > 32 warps
+                const double* p = part + (size_t)rec_index(w, e) * PART_STRIDE;
                 double b[NACC];
 #pragma unroll
                 for (int k = 0; k < NACC; ++k) b[k] = p[1 + k];
@@ -268,25 +275,25 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
                 nv += p[1 + NACC];
             }
         }
-        for (int o = lpe >> 1; o > 0; o >>= 1) {   // fixed butterfly over the event's lanes: deterministic
-            double b[NACC];
-            const double m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        // The event's lanes: common shift first (max over the lanes), every lane rescales its own sums once, then a
+        // plain xor butterfly of additions - a + b is commutative, so both partners of every step hold identical bits
+        // and the result is deterministic.  (Round 1 merged (shift, sums) pairs at every step: two exponentials and a
+        // select chain per step instead of one exponential in total.)
+        double mx = m;
+        for (int o = lpe >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        {
+            const double sc = (m == -INFINITY) ? 0.0 : exp(m - mx);
+            a[0] *= sc;
+            a[1] *= sc * sc;
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) b[k] = __shfl_xor_sync(0xffffffffu, a[k], o);
-            nv += __shfl_xor_sync(0xffffffffu, nv, o);
-            // both partners must end with identical bits: merge in (lower lane, upper lane) order
-            if (sub & o) {
-                double mm = m2, aa[NACC];
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) aa[k] = b[k];
-                lse_merge(mm, aa, m, a);
-                m = mm;
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) a[k] = aa[k];
-            } else {
-                lse_merge(m, a, m2, b);
-            }
+            for (int k = 2; k < NACC; ++k) a[k] *= sc;
         }
+        for (int o = lpe >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+            nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        }
+        m = mx;
         if (e < nobs && sub == 0) {
             if (m == -INFINITY || !(a[0] > 0.0)) {   // no finite-weight sample: logsumexp = -inf (reference: same)
                 ev[2] = 1.0;
@@ -307,12 +314,12 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         }
     } else {
         // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps owning its groups
-        const bool has_sel = wk.n_groups > wk.n_evt_groups;
-        const int64_t ws0 = has_sel ? wk.n_evt_groups / wk.gpw : 0;
-        const int64_t ws1 = has_sel ? (wk.n_groups - 1) / wk.gpw : -1;
+        const bool has_sel = n_groups > n_evt_groups;
+        const int ws0 = has_sel ? n_evt_groups / gpw : 0;
+        const int ws1 = has_sel ? (n_groups - 1) / gpw : -1;
         double mx = -INFINITY;
-        for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS)
-            mx = fmax(mx, part[record_of(wk, rec_off, w, nobs) * PART_STRIDE]);
+        for (int w = ws0 + tid; w <= ws1; w += EPI_THREADS)
+            mx = fmax(mx, part[(size_t)rec_index(w, nobs) * PART_STRIDE]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((tid & 31) == 0) red[tid >> 5] = mx;
@@ -327,8 +334,8 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         double sv[NACC + 1];
 #pragma unroll
         for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
-        for (int64_t w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
-            const double* p = part + record_of(wk, rec_off, w, nobs) * PART_STRIDE;
+        for (int w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
+            const double* p = part + (size_t)rec_index(w, nobs) * PART_STRIDE;
             if (p[0] == -INFINITY) continue;
             const double s = exp(p[0] - mx);
             sv[0] += p[1] * s;

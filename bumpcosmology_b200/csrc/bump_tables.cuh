@@ -202,7 +202,7 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
         const double lz = (k >= NZ - 1) ? LOG_ZMAX1 : k * ZSTEP;   // np.linspace(0, log(101), 1024), :230
         z[q] = expm1(lz);
         const double opz = 1.0 + z[q];
-        const double lopz = log(opz);
+        const double lopz = lz;   // log(1 + expm1(lz)): the grid IS uniform in log(1+z) (saves a libm log on the chain)
         D de = dexp((3.0 * (1.0 + w + wa)) * lopz);               // opz**(3(1+w)), :256
         if (use_wa) de = de * dexp(wa * (-3.0 * z[q] / opz));     // CPL extension (no reference counterpart)
         D E = dsqrt(Om * (opz * opz * opz) + (1.0 - Om) * de);
@@ -254,7 +254,7 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
 #pragma unroll
         for (int c = 0; c < 4; ++c) sm[64 + c] = p4[c];
     }
-    cluster.sync();   // the totals have been read: their slots may be reused, and nobody exits before this point
+    __syncthreads();  // sm[64..67]; the totals' slots are not reused, and no block exits before the barriers below
     double base[4] = {sm[64], sm[65], sm[66], sm[67]};
     for (int ww = 0; ww < warp; ++ww) {
 #pragma unroll
@@ -300,7 +300,16 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
     pack_cosmology_bin(k, lo, hi, me, blob, ec, j0, j1);
     {
         unsigned short* srch = reinterpret_cast<unsigned short*>(blob + OFF_SRCH);
-        for (int src = 0; src < 32; ++src) {   // the 32 ranges of this warp, each filled by all of its lanes
+        // short ranges (almost all: a bin is a handful of buckets wide) by their own thread, long ones (the first
+        // knots: hundreds of buckets each) by all lanes of the warp
+        constexpr int LONG_RANGE = 16;
+        const bool is_long = j1 - j0 > LONG_RANGE;
+        if (!is_long)
+            for (int j = j0; j < j1; ++j) srch[j] = (unsigned short)(j == 0 ? 0 : k);
+        unsigned int todo = __ballot_sync(0xffffffffu, is_long);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
             const int a0 = __shfl_sync(0xffffffffu, j0, src), a1 = __shfl_sync(0xffffffffu, j1, src);
             const int bb = __shfl_sync(0xffffffffu, k, src);
             for (int j = a0 + lane; j < a1; j += 32) srch[j] = (unsigned short)(j == 0 ? 0 : bb);
@@ -313,9 +322,7 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
 // Called by 7 threads: thread v carries the tangent with respect to variable v of (a, b, c, mpisn, mbhmax, sigma, fpl)
 // (a Dual<1> each instead of one thread with a Dual<7>: the serial chain is ~3x shorter); thread 0 also writes the
 // primal values.  gtab = [6][NM] copy of aux[AUX_G ...] (shared memory); aux_ = the global workspace.
-__device__ void build_scalars(const double* th, const double* aux_, const double* gtab, const EvalConsts ec,
-                              double* scal, const int v) {
-    const CgView aux{aux_};
+__device__ void build_scalars(const double* th, const double* gtab, double* scal, double* s_tmp, const int v) {
     typedef Dual<1> D;
     const int map5[5] = {0, 1, 3, 4, 5};   // (a, b, mpisn, mbhmax, sigma) -> variable index
     int q5 = -1;                           // this thread's row in the PISN tangent table, if any
@@ -361,45 +368,58 @@ __device__ void build_scalars(const double* th, const double* aux_, const double
     if (q5 >= 0) scal[S_LPN_D0 + q5] = lpn.d[0];
     scal[S_LN_D0 + v] = ln.d[0];
     if (v != 0) return;
-    // rate normalisation: log_norm = -self(zref=0) (:168,173)
-    const double kappa = th[T_KAPPA], zp = th[T_ZP];
-    const double lopzp = log1p(zp);
-    const double r0 = exp(-kappa * lopzp);
-    const double lnV = log1p(r0);
-    const double sig0 = r0 / (1.0 + r0);
+    // the scalars that hang on the chain above; s_tmp[0] = log_norm for S_CONST (combined by the caller)
+    s_tmp[0] = ln.v;
+    scal[S_LPN] = lpn.v;
+    scal[S_LOG_NORM] = ln.v;
+    scal[S_EXP_LPN] = exp(lpn.v);
+    scal[S_C2] = 2.0 * exp(lpn.v);
+    scal[S_LOG_C2] = LN2 + lpn.v;
+}
 
+// The scalars that do not need the PISN table, by two more threads beside the seven chains (role 7: the rate
+// normalisation log_norm = -self(zref = 0), intensity_models.py:168,173; role 8: theta-only numbers): the serial tail
+// of the prologue is the longest of the nine chains instead of their sum.
+__device__ void build_scalars_extra(const double* th, const double* aux_, const EvalConsts ec, double* scal,
+                                    double* s_tmp, const int role) {
+    if (role == 7) {
+        const double kappa = th[T_KAPPA], zp = th[T_ZP];
+        const double lopzp = log1p(zp);
+        const double r0 = exp(-kappa * lopzp);
+        const double lnV = log1p(r0);
+        const double sig0 = r0 / (1.0 + r0);
+        s_tmp[1] = lnV;
+        scal[S_KAPPA] = kappa;
+        scal[S_ZP] = zp;
+        scal[S_LOPZP] = lopzp;
+        scal[S_RATE_LOG_NORM] = lnV;
+        scal[S_LNV_KAPPA] = -sig0 * lopzp;
+        scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
+        return;
+    }
+    const CgView aux{aux_};
+    const double M = th[T_MBHMAX], top = M + 7.0 * th[T_SIGMA];
     scal[S_H] = th[T_H];
     scal[S_INV_H] = 1.0 / th[T_H];
     scal[S_C] = th[T_C];
-    scal[S_M] = M.v;
-    scal[S_LOG_M] = log(M.v);
-    scal[S_INV_DM] = 1.0 / (M.v * TURNON_WIDTH);
-    scal[S_LPN] = lpn.v;
-    scal[S_TOP] = top.v;
-    scal[S_INV_DMBH] = (NM - 1) / (top.v - MIN_BH_MASS);
-    scal[S_INV_TOPM3] = 1.0 / (top.v - MIN_BH_MASS);
+    scal[S_M] = M;
+    scal[S_LOG_M] = log(M);
+    scal[S_INV_DM] = 1.0 / (M * TURNON_WIDTH);
+    scal[S_TOP] = top;
+    const double inv_dmbh = (NM - 1) / (top - MIN_BH_MASS);
+    scal[S_INV_DMBH] = inv_dmbh;
+    scal[S_INV_TOPM3] = 1.0 / (top - MIN_BH_MASS);
     scal[S_BETA] = th[T_BETA];
     scal[S_LAM] = th[T_LAM];
-    scal[S_KAPPA] = kappa;
-    scal[S_ZP] = zp;
-    scal[S_LOPZP] = lopzp;
     scal[S_DL_LAST] = aux[AUX_DL + NZ - 1];
-    scal[S_FPL] = fpl.v;
-    scal[S_CONST] = 2.0 * ln.v + lnV - th[T_BETA] * LOG_MREF_PAIR;
-    scal[S_LOG_NORM] = ln.v;
-    scal[S_RATE_LOG_NORM] = lnV;
-    scal[S_LNV_KAPPA] = -sig0 * lopzp;
-    scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
+    scal[S_FPL] = th[T_FPL];
     scal[S_LOG_NSAMP] = ec.log_nsamp;
     scal[S_LOG_NDRAW] = ec.log_ndraw;
     scal[S_USE_WA] = (double)ec.use_wa;
     scal[S_FIXED] = (double)ec.fixed;
     scal[S_DL_FIRST] = aux[AUX_DL + 0];
-    scal[S_EXP_LPN] = exp(lpn.v);
     scal[S_ZEPS] = expm1(ZSTEP);
-    scal[S_C2] = 2.0 * exp(lpn.v);
-    scal[S_LOG_C2] = LN2 + lpn.v;
-    scal[S_POS0] = -MIN_BH_MASS * scal[S_INV_DMBH];
+    scal[S_POS0] = -MIN_BH_MASS * inv_dmbh;
     scal[S_LAM2] = th[T_LAM] - 2.0;
     scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
 }
@@ -471,8 +491,12 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
     __syncthreads();
     if (threadIdx.x < 32) {
-        if (threadIdx.x < 7) build_scalars(th, aux, gtab, ec, blob + OFF_SCAL, threadIdx.x);
+        double* s_tmp = sm + 6 * NM;   // behind the table copy
+        if (threadIdx.x < 7) build_scalars(th, gtab, blob + OFF_SCAL, s_tmp, threadIdx.x);
+        else if (threadIdx.x < 9) build_scalars_extra(th, aux, ec, blob + OFF_SCAL, s_tmp, threadIdx.x);
+        __syncwarp();
         if (threadIdx.x == 0) {
+            blob[OFF_SCAL + S_CONST] = 2.0 * s_tmp[0] + s_tmp[1] - th[T_BETA] * LOG_MREF_PAIR;
             // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
             // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
             // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
