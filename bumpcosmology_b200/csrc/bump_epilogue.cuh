@@ -228,13 +228,14 @@ __device__ __forceinline__ void epi_block_sum(double (&v)[NV], double* red) {
 // part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt)) is covered
 // by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
 //   blocks 0 .. nb_evt-1 : one thread per event -> logsumexp, Neff, normalised features; block sum -> slot[b]
-//   block  nb_evt        : the injection records -> slot[nb_evt]
+//   blocks nb_evt .. nb_evt+nb_sel-1 : a slice of the injection records each -> (shift, sums) in slot[b]
 //   last block to finish : fixed-order sum of the slots -> this rank's partial; with `out_header` non-null
 //                          (single rank) it also finalizes, saving a launch.
 constexpr int EPI_SLOT = 24;
 __global__ void __launch_bounds__(EPI_THREADS)
 epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off, const Work wk, const double nsel,
-                const int lpe /* lanes per event: power of two <= 32 */, const double* __restrict__ blob,
+                const int lpe /* lanes per event: power of two <= 32 */, const int nb_sel /* injection blocks */,
+                const double* __restrict__ blob,
                 double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
                 double* __restrict__ partial, double* __restrict__ out_header, const Peers* __restrict__ peers,
                 unsigned long long* __restrict__ exchange_state, unsigned long long* __restrict__ tl) {
@@ -314,9 +315,14 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         }
     } else {
         // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps owning its groups
+        // (the warps that own injection groups are split evenly over the nb_sel injection blocks: one block was the
+        // longest-running of the kernel at GWTC-3 size)
         const bool has_sel = n_groups > n_evt_groups;
-        const int ws0 = has_sel ? n_evt_groups / gpw : 0;
-        const int ws1 = has_sel ? (n_groups - 1) / gpw : -1;
+        const int wa0 = has_sel ? n_evt_groups / gpw : 0;
+        const int wa1 = has_sel ? (n_groups - 1) / gpw : -1;
+        const int per = (wa1 - wa0 + nb_sel) / nb_sel;                 // ceil((wa1 - wa0 + 1) / nb_sel)
+        const int ws0 = wa0 + ((int)blockIdx.x - nb_evt) * per;
+        const int ws1 = min(wa1, ws0 + per - 1);
         double mx = -INFINITY;
         for (int w = ws0 + tid; w <= ws1; w += EPI_THREADS)
             mx = fmax(mx, part[(size_t)rec_index(w, nobs) * PART_STRIDE]);
@@ -395,9 +401,22 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
             else if (tid >= P_FSUM0 && tid < P_FSUM0 + NFEAT) v = red[3 + tid - P_FSUM0];
             else if (tid == P_NVALID_EVT) v = red[1];
             else if (tid == P_NDEAD_EVT) v = red[2];
-            else if (tid == P_SEL_M) v = __ldcg(ss);
-            else if (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) v = __ldcg(ss + 1 + tid - P_SEL_ACC0);
-            else if (tid == P_NVALID_SEL) v = __ldcg(ss + 1 + NACC);
+            else if (tid == P_SEL_M || (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) || tid == P_NVALID_SEL) {
+                // rank-order merge of the injection blocks' (shift, sums): common shift, then a fixed-order sum
+                double M = -INFINITY;
+                for (int b = 0; b < nb_sel; ++b) M = fmax(M, __ldcg(ss + (size_t)b * EPI_SLOT));
+                if (tid == P_SEL_M) {
+                    v = M;
+                } else {
+                    const int k = (tid == P_NVALID_SEL) ? NACC : tid - P_SEL_ACC0;
+                    for (int b = 0; b < nb_sel; ++b) {
+                        const double mb = __ldcg(ss + (size_t)b * EPI_SLOT);
+                        if (mb == -INFINITY) continue;
+                        const double sc = (k == NACC) ? 1.0 : exp(mb - M);
+                        v += __ldcg(ss + (size_t)b * EPI_SLOT + 1 + k) * (k == 1 ? sc * sc : sc);
+                    }
+                }
+            }
             else if (tid == P_NSEL) v = nsel;
         } else {
             v = __ldcg(blob + OFF_SCAL + tid - P_SCAL0);

@@ -216,7 +216,7 @@ struct bump_ctx {
     // plan
     bool plan_dirty = true;
     Work work{};
-    int nrecords = 0, grid = 0, sm_count = 0, lpe = 1;
+    int nrecords = 0, grid = 0, sm_count = 0, lpe = 1, nb_sel = 1;
     int* d_rec_off = nullptr;
     double* d_part = nullptr;
     double* d_slots = nullptr;
@@ -348,7 +348,12 @@ int build_plan(bump_ctx* c) {
     CK(cudaMalloc(&c->d_rec_off, sizeof(int) * rec_off.size()));
     CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max(1, c->nrecords)));
     const int epb = EPI_THREADS / c->lpe;
-    CK(cudaMalloc(&c->d_slots, sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + 1)));
+    {   // injection blocks of the epilogue: one per 256 warps that own injection groups, at most 8
+        const int64_t sel_groups = w.n_groups - w.n_evt_groups;
+        const int64_t sel_warps = sel_groups > 0 ? (w.n_groups - 1) / w.gpw - w.n_evt_groups / w.gpw + 1 : 0;
+        c->nb_sel = (int)std::min<int64_t>(8, std::max<int64_t>(1, (sel_warps + EPI_THREADS - 1) / EPI_THREADS));
+    }
+    CK(cudaMalloc(&c->d_slots, sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + c->nb_sel)));
     CK(cudaMalloc(&c->d_out, sizeof(double) * c->out_len));
     CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
     CK(cudaMemcpy(c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size(), cudaMemcpyHostToDevice));
@@ -405,8 +410,8 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
-    epilogue_kernel<<<nb_evt + 1, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols, c->lpe,
-                                                       c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
+    epilogue_kernel<<<nb_evt + c->nb_sel, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols,
+                                                               c->lpe, c->nb_sel, c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
                                                        fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl);
     CK(cudaGetLastError());
     return BUMP_OK;

@@ -275,7 +275,9 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
     double me[COS_VALS] = {z[0], dl.v, ddl.v, dvc.v, dl.d[0], dl.d[1], dl.d[2], ddl.d[0], ddl.d[1], ddl.d[2],
                            dvc.d[0], dvc.d[1], dvc.d[2]};
 #pragma unroll
-    for (int r = 0; r < COS_VALS; ++r) aux[r * NZ + k] = me[r];   // raw knots (bump_debug_tables, scalars)
+    for (int r = 0; r < COS_VALS; ++r) aux[r * NZ + k] = me[r];   // raw knots (bump_debug_tables)
+    if (k == 0) blob[OFF_SCAL + S_DL_FIRST] = dl.v;
+    if (k == NZ - 1) blob[OFF_SCAL + S_DL_LAST] = dl.v;
     static_assert(AUX_ZG == 0 && AUX_DL == NZ && AUX_DDL == 2 * NZ && AUX_DVC == 3 * NZ && AUX_TAN == 4 * NZ,
                   "aux order of the 13 cosmology value sets");
     // ---- packed per-bin records, straight from the registers: bin b = [knot b, knot b+1] needs the right neighbour's
@@ -380,8 +382,8 @@ __device__ void build_scalars(const double* th, const double* gtab, double* scal
 // The scalars that do not need the PISN table, by two more threads beside the seven chains (role 7: the rate
 // normalisation log_norm = -self(zref = 0), intensity_models.py:168,173; role 8: theta-only numbers): the serial tail
 // of the prologue is the longest of the nine chains instead of their sum.
-__device__ void build_scalars_extra(const double* th, const double* aux_, const EvalConsts ec, double* scal,
-                                    double* s_tmp, const int role) {
+__device__ void build_scalars_extra(const double* th, const EvalConsts ec, double* scal, double* s_tmp,
+                                    const int role) {
     if (role == 7) {
         const double kappa = th[T_KAPPA], zp = th[T_ZP];
         const double lopzp = log1p(zp);
@@ -397,7 +399,6 @@ __device__ void build_scalars_extra(const double* th, const double* aux_, const 
         scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
         return;
     }
-    const CgView aux{aux_};
     const double M = th[T_MBHMAX], top = M + 7.0 * th[T_SIGMA];
     scal[S_H] = th[T_H];
     scal[S_INV_H] = 1.0 / th[T_H];
@@ -411,13 +412,11 @@ __device__ void build_scalars_extra(const double* th, const double* aux_, const 
     scal[S_INV_TOPM3] = 1.0 / (top - MIN_BH_MASS);
     scal[S_BETA] = th[T_BETA];
     scal[S_LAM] = th[T_LAM];
-    scal[S_DL_LAST] = aux[AUX_DL + NZ - 1];
     scal[S_FPL] = th[T_FPL];
     scal[S_LOG_NSAMP] = ec.log_nsamp;
     scal[S_LOG_NDRAW] = ec.log_ndraw;
     scal[S_USE_WA] = (double)ec.use_wa;
     scal[S_FIXED] = (double)ec.fixed;
-    scal[S_DL_FIRST] = aux[AUX_DL + 0];
     scal[S_ZEPS] = expm1(ZSTEP);
     scal[S_POS0] = -MIN_BH_MASS * inv_dmbh;
     scal[S_LAM2] = th[T_LAM] - 2.0;
@@ -443,14 +442,15 @@ __device__ void pack_mass_records(const double* __restrict__ gtab /* shared copy
 //                        are one cluster and chain their cumulative trapezoid through distributed shared memory
 //   blocks 4..4+NM-1   : row i of the PISN pile-up table  (intensity_models.py:96-108, LogDNDMPISN.__post_init__)
 //                        and pack their bins of the cosmology records and of the d_L bucket table themselves
-//   the block that finishes last (ticket): packed mass records (warps 1..7) and the scalars
-//                        (intensity_models.py:134-138,167-168; 7 threads of warp 0) -> the blob the streaming kernel stages
+//   the row block that finishes last (rows ticket): packed mass records (warps 1..7) and the scalars
+//                        (intensity_models.py:134-138,167-168; 9 threads of warp 0) -> the blob the streaming kernel stages
+//   the block that finishes last of all (ticket): the validity flag
 constexpr int PRO_BLOCKS = NM + COS_CHUNKS;
 static_assert(PRO_BLOCKS % COS_CHUNKS == 0, "the grid is a whole number of clusters");
 
 __global__ void __cluster_dims__(COS_CHUNKS, 1, 1) __launch_bounds__(PRO_THREADS)
 prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
-                unsigned int* __restrict__ flags /* [0] ticket, [1] bad */, const EvalConsts ec,
+                unsigned int* __restrict__ flags /* [0] ticket, [1] bad, [2] rows ticket */, const EvalConsts ec,
                 unsigned long long* __restrict__ tl) {
     __shared__ double sm[PRO_SMEM_DOUBLES];
     __shared__ double th[NTHETA_MAX];
@@ -476,44 +476,53 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
-    // ---- last block: everything the other blocks wrote is visible after the ticket
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(flags, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) {
-        timeline_end(tl, TL_PROLOGUE);
-        return;
-    }
-    __threadfence();
-    timeline_begin(tl, TL_PRO_LAST);
-    double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
-    for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double* s_tmp = sm + 6 * NM;   // behind the table copy
-        if (threadIdx.x < 7) build_scalars(th, gtab, blob + OFF_SCAL, s_tmp, threadIdx.x);
-        else if (threadIdx.x < 9) build_scalars_extra(th, aux, ec, blob + OFF_SCAL, s_tmp, threadIdx.x);
-        __syncwarp();
-        if (threadIdx.x == 0) {
-            blob[OFF_SCAL + S_CONST] = 2.0 * s_tmp[0] + s_tmp[1] - th[T_BETA] * LOG_MREF_PAIR;
-            // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
-            // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
-            // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
-            // last two bins).  That takes roughly h > 7 or h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).
-            const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
-            const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
-            unsigned int f = flags[1];
-            if (!ec.fixed && (!(__ldcg(aux + AUX_DL + 2) >= first_hi) || !(__ldcg(aux + AUX_DL + NZ - 3) <= last_lo))) f = 1u;
-            blob[OFF_SCAL + S_BAD] = (f != 0u) ? 1.0 : 0.0;
-            flags[0] = 0u;   // re-arm the ticket and the bad flag for the next evaluation
-            flags[1] = 0u;
+    // ---- the LAST ROW block (rows ticket): once all 256 PISN rows exist, the scalars (seven forward-mode chains of
+    // ~1000 dependent FP64 instructions each: the longest serial piece of the prologue) and the packed mass records.
+    // It does not wait for the cosmology cluster, which is still at work then (rows: ~5 us, cosmology: ~9.5 us).
+    if (!is_cos) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(flags + 2, 1u) == NM - 1);
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            timeline_begin(tl, TL_PRO_LAST);
+            double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
+            for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double* s_tmp = sm + 6 * NM;   // behind the table copy
+                if (threadIdx.x < 7) build_scalars(th, gtab, blob + OFF_SCAL, s_tmp, threadIdx.x);
+                else if (threadIdx.x < 9) build_scalars_extra(th, ec, blob + OFF_SCAL, s_tmp, threadIdx.x);
+                __syncwarp();
+                if (threadIdx.x == 0) {
+                    blob[OFF_SCAL + S_CONST] = 2.0 * s_tmp[0] + s_tmp[1] - th[T_BETA] * LOG_MREF_PAIR;
+                    flags[2] = 0u;   // re-arm the rows ticket
+                }
+            } else {
+                pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
+            }
+            __syncthreads();
+            timeline_end(tl, TL_PRO_LAST);
         }
-    } else {
-        pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
     }
+    // ---- the block that finishes last of all (global ticket): the validity flag, and re-arming
+    __threadfence();
     __syncthreads();
-    timeline_end(tl, TL_PRO_LAST);
+    if (threadIdx.x == 0 && atomicAdd(flags, 1u) == gridDim.x - 1) {
+        __threadfence();
+        // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
+        // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
+        // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
+        // last two bins).  That takes roughly h > 7 or h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).
+        const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
+        const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
+        unsigned int f = atomicOr(flags + 1, 0u);
+        if (!ec.fixed && (!(__ldcg(aux + AUX_DL + 2) >= first_hi) || !(__ldcg(aux + AUX_DL + NZ - 3) <= last_lo))) f = 1u;
+        blob[OFF_SCAL + S_BAD] = (f != 0u) ? 1.0 : 0.0;
+        flags[0] = 0u;   // re-arm the ticket and the bad flag for the next evaluation
+        flags[1] = 0u;
+    }
     timeline_end(tl, TL_PROLOGUE);
 }
 
