@@ -410,6 +410,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
 
     const int lane = threadIdx.x & 31;
     const uint32_t rep = (uint32_t)(lane & (EXPT_REPL - 1)) << 3;   // this lane's copy of the exp-table entries
+    uint64_t l2_stream_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream_policy));
     // The warp index through a shuffle from lane 0: the same value, but one the compiler KNOWS to be warp-uniform.
     // Everything derived from it (the warp's group range, the loop trip count, event boundaries) is then uniform too,
     // the sample loop is convergent code, and ptxas keeps the theta-dependent scalars in UNIFORM registers, which FP64
@@ -451,9 +453,17 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     auto load_half = [&](const double* p) {   // p = block + lane (x half) or block + 32 + lane (y half)
         // volatile: keeps the load where it is written (ptxas otherwise sinks it to its first use to save
         // registers, which exposes the full L2 latency once per group)
-        auto ld = [](const double* a) {
+        // L2 policy evict_first: the columns are read once per evaluation, and at O5 size one pass sweeps far more than
+        // the 126 MB of L2.  Marked this way they are the first lines to go, so what the other kernels of the evaluation
+        // need again - the tables, the per-warp records, and the CODE of the prologue / epilogue tails - survives the
+        // sweep (their single-warp tails ran twice as long after an O5-size pass: instruction fetches from DRAM).
+        auto ld = [&](const double* a) {
             double v;
+#ifdef BUMP_NO_L2_POLICY
             asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
+#else
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(l2_stream_policy));
+#endif
             return v;
         };
         Half h;

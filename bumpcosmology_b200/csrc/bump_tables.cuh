@@ -321,106 +321,121 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
 }
 
 // ---------------------------------------------------------------- scalars
-// Called by 7 threads: thread v carries the tangent with respect to variable v of (a, b, c, mpisn, mbhmax, sigma, fpl)
-// (a Dual<1> each instead of one thread with a Dual<7>: the serial chain is ~3x shorter); thread 0 also writes the
-// primal values.  gtab = [6][NM] copy of aux[AUX_G ...] (shared memory); aux_ = the global workspace.
-__device__ void build_scalars(const double* th, const double* gtab, double* scal, double* s_tmp, const int v) {
+// Called by ALL 32 lanes of one warp.  log_pl_norm (:136) and log_norm (:138, :140-151) with their tangents are seven
+// forward-mode chains, one per variable v of (a, b, c, mpisn, mbhmax, sigma, fpl) (a Dual<1> each instead of one thread
+// with a Dual<7>), and every chain is split over three lanes, lane = 3 v + sub, that evaluate its independent pieces
+//   sub 0: log_pl_norm = log fpl + PISN(mbhmax)      sub 1: PISN(mref)      sub 2: turn-on(mref) - c log(mref / mbhmax)
+// before lane 3 v joins them with two shuffles (this is the longest serial piece of the whole prologue: ~1000 dependent
+// FP64 instructions per chain unsplit).  Lane 21 derives the rate normalisation (-self(zref = 0), :168,173), lane 22
+// the theta-only numbers.  gtab = [6][NM] copy of aux[AUX_G ...] in shared memory.
+__device__ void build_scalars(const double* th, const double* gtab, const EvalConsts ec, double* scal, const int lane) {
     typedef Dual<1> D;
-    const int map5[5] = {0, 1, 3, 4, 5};   // (a, b, mpisn, mbhmax, sigma) -> variable index
-    int q5 = -1;                           // this thread's row in the PISN tangent table, if any
+    const int v = lane / 3, sub = lane - 3 * v;
+    D piece(0.0);        // this lane's piece of chain v
+    double lnV = 0.0;    // lane 21
+    if (lane < 21) {
+        const int map5[5] = {0, 1, 3, 4, 5};   // (a, b, mpisn, mbhmax, sigma) -> variable index
+        int q5 = -1;                           // this chain's row in the PISN tangent table, if any
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
-        if (map5[q] == v) q5 = q;
-    auto seed = [&](const double x, const int var) {
-        D r(x);
-        r.d[0] = (var == v) ? 1.0 : 0.0;
-        return r;
-    };
-    D c = seed(th[T_C], 2), M = seed(th[T_MBHMAX], 4), sg = seed(th[T_SIGMA], 5), fpl = seed(th[T_FPL], 6);
-    D top = M + 7.0 * sg;
-    auto knot = [&](int k) -> D {
-        const double s = (double)k / (NM - 1);
-        return (k == NM - 1) ? top : (MIN_BH_MASS * (1.0 - s) + top * s);
-    };
-    auto Gk = [&](int k) -> D {
-        D g(gtab[k]);
-        g.d[0] = (q5 >= 0) ? gtab[(q5 + 1) * NM + k] : 0.0;
-        return g;
-    };
-    // jnp.interp(m, mbh_grid, log_dN_grid), differentiable in m, the knots and the values (:110-111)
-    auto pisn = [&](const D& m) -> D {
-        int i = (int)floor((m.v - MIN_BH_MASS) / (top.v - MIN_BH_MASS) * (NM - 1)) + 1;
-        i = min(max(i, 1), NM - 1);
-        while (i < NM - 1 && knot(i).v <= m.v) ++i;       // i = clip(#{knots <= m}, 1, n-1)
-        while (i > 1 && knot(i - 1).v > m.v) --i;
-        D x0 = knot(i - 1), x1 = knot(i), f0 = Gk(i - 1), f1 = Gk(i);
-        D f = f0 + ((m - x0) / (x1 - x0)) * (f1 - f0);
-        if (m.v < knot(0).v) f = Gk(0);
-        if (m.v > top.v) f = Gk(NM - 1);
-        return f;
-    };
-    D lpn = dlog(fpl) + pisn(M);                                   // :136
-    // log_norm = -(self(mref) + log(mref)) with log_norm = 0 inside (:138, :140-151)
-    D mref(MREF);
-    D P = (MREF <= MIN_BH_MASS || MREF >= top.v) ? D(-INFINITY) : pisn(mref);
-    D turn = LN2 - dlog1p(dexp(-(mref - M) / (M * TURNON_WIDTH)));  // :52-54
-    D Q = -c * dlog(mref / M) + lpn + turn;
-    D A0 = (MREF < MBH_MIN) ? D(-INFINITY) : dlogaddexp(P, Q);
-    D ln = -(A0 + log(MREF));
-    if (q5 >= 0) scal[S_LPN_D0 + q5] = lpn.d[0];
-    scal[S_LN_D0 + v] = ln.d[0];
-    if (v != 0) return;
-    // the scalars that hang on the chain above; s_tmp[0] = log_norm for S_CONST (combined by the caller)
-    s_tmp[0] = ln.v;
-    scal[S_LPN] = lpn.v;
-    scal[S_LOG_NORM] = ln.v;
-    scal[S_EXP_LPN] = exp(lpn.v);
-    scal[S_C2] = 2.0 * exp(lpn.v);
-    scal[S_LOG_C2] = LN2 + lpn.v;
-}
-
-// The scalars that do not need the PISN table, by two more threads beside the seven chains (role 7: the rate
-// normalisation log_norm = -self(zref = 0), intensity_models.py:168,173; role 8: theta-only numbers): the serial tail
-// of the prologue is the longest of the nine chains instead of their sum.
-__device__ void build_scalars_extra(const double* th, const EvalConsts ec, double* scal, double* s_tmp,
-                                    const int role) {
-    if (role == 7) {
+        for (int q = 0; q < 5; ++q)
+            if (map5[q] == v) q5 = q;
+        auto seed = [&](const double x, const int var) {
+            D r(x);
+            r.d[0] = (var == v) ? 1.0 : 0.0;
+            return r;
+        };
+        const D c = seed(th[T_C], 2), M = seed(th[T_MBHMAX], 4), sg = seed(th[T_SIGMA], 5), fpl = seed(th[T_FPL], 6);
+        const D top = M + 7.0 * sg;
+        auto knot = [&](int k) -> D {
+            const double s = (double)k / (NM - 1);
+            return (k == NM - 1) ? top : (MIN_BH_MASS * (1.0 - s) + top * s);
+        };
+        auto Gk = [&](int k) -> D {
+            D g(gtab[k]);
+            g.d[0] = (q5 >= 0) ? gtab[(q5 + 1) * NM + k] : 0.0;
+            return g;
+        };
+        // jnp.interp(m, mbh_grid, log_dN_grid), differentiable in m, the knots and the values (:110-111)
+        auto pisn = [&](const D& m) -> D {
+            int i = (int)floor((m.v - MIN_BH_MASS) / (top.v - MIN_BH_MASS) * (NM - 1)) + 1;
+            i = min(max(i, 1), NM - 1);
+            while (i < NM - 1 && knot(i).v <= m.v) ++i;       // i = clip(#{knots <= m}, 1, n-1)
+            while (i > 1 && knot(i - 1).v > m.v) --i;
+            D x0 = knot(i - 1), x1 = knot(i), f0 = Gk(i - 1), f1 = Gk(i);
+            D f = f0 + ((m - x0) / (x1 - x0)) * (f1 - f0);
+            if (m.v < knot(0).v) f = Gk(0);
+            if (m.v > top.v) f = Gk(NM - 1);
+            return f;
+        };
+        const D mref(MREF);
+        if (sub == 0) {
+            piece = dlog(fpl) + pisn(M);                                                        // log_pl_norm, :136
+        } else if (sub == 1) {
+            piece = (MREF <= MIN_BH_MASS || MREF >= top.v) ? D(-INFINITY) : pisn(mref);         // :144-145
+        } else {
+            piece = LN2 - dlog1p(dexp(-(mref - M) / (M * TURNON_WIDTH))) - c * dlog(mref / M);  // :52-54, :147
+        }
+    } else if (lane == 21) {
         const double kappa = th[T_KAPPA], zp = th[T_ZP];
         const double lopzp = log1p(zp);
         const double r0 = exp(-kappa * lopzp);
-        const double lnV = log1p(r0);
+        lnV = log1p(r0);
         const double sig0 = r0 / (1.0 + r0);
-        s_tmp[1] = lnV;
         scal[S_KAPPA] = kappa;
         scal[S_ZP] = zp;
         scal[S_LOPZP] = lopzp;
         scal[S_RATE_LOG_NORM] = lnV;
         scal[S_LNV_KAPPA] = -sig0 * lopzp;
         scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
-        return;
+    } else if (lane == 22) {
+        const double M = th[T_MBHMAX], top = M + 7.0 * th[T_SIGMA];
+        scal[S_H] = th[T_H];
+        scal[S_INV_H] = 1.0 / th[T_H];
+        scal[S_C] = th[T_C];
+        scal[S_M] = M;
+        scal[S_LOG_M] = log(M);
+        scal[S_INV_DM] = 1.0 / (M * TURNON_WIDTH);
+        scal[S_TOP] = top;
+        const double inv_dmbh = (NM - 1) / (top - MIN_BH_MASS);
+        scal[S_INV_DMBH] = inv_dmbh;
+        scal[S_INV_TOPM3] = 1.0 / (top - MIN_BH_MASS);
+        scal[S_BETA] = th[T_BETA];
+        scal[S_LAM] = th[T_LAM];
+        scal[S_FPL] = th[T_FPL];
+        scal[S_LOG_NSAMP] = ec.log_nsamp;
+        scal[S_LOG_NDRAW] = ec.log_ndraw;
+        scal[S_USE_WA] = (double)ec.use_wa;
+        scal[S_FIXED] = (double)ec.fixed;
+        scal[S_ZEPS] = expm1(ZSTEP);
+        scal[S_POS0] = -MIN_BH_MASS * inv_dmbh;
+        scal[S_LAM2] = th[T_LAM] - 2.0;
+        scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
     }
-    const double M = th[T_MBHMAX], top = M + 7.0 * th[T_SIGMA];
-    scal[S_H] = th[T_H];
-    scal[S_INV_H] = 1.0 / th[T_H];
-    scal[S_C] = th[T_C];
-    scal[S_M] = M;
-    scal[S_LOG_M] = log(M);
-    scal[S_INV_DM] = 1.0 / (M * TURNON_WIDTH);
-    scal[S_TOP] = top;
-    const double inv_dmbh = (NM - 1) / (top - MIN_BH_MASS);
-    scal[S_INV_DMBH] = inv_dmbh;
-    scal[S_INV_TOPM3] = 1.0 / (top - MIN_BH_MASS);
-    scal[S_BETA] = th[T_BETA];
-    scal[S_LAM] = th[T_LAM];
-    scal[S_FPL] = th[T_FPL];
-    scal[S_LOG_NSAMP] = ec.log_nsamp;
-    scal[S_LOG_NDRAW] = ec.log_ndraw;
-    scal[S_USE_WA] = (double)ec.use_wa;
-    scal[S_FIXED] = (double)ec.fixed;
-    scal[S_ZEPS] = expm1(ZSTEP);
-    scal[S_POS0] = -MIN_BH_MASS * inv_dmbh;
-    scal[S_LAM2] = th[T_LAM] - 2.0;
-    scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
+    __syncwarp();
+    // join: lane 3 v (sub 0) takes PISN(mref) from lane 3 v + 1 and the power-law piece from lane 3 v + 2
+    D P, T;
+    P.v = __shfl_down_sync(0xffffffffu, piece.v, 1), P.d[0] = __shfl_down_sync(0xffffffffu, piece.d[0], 1);
+    T.v = __shfl_down_sync(0xffffffffu, piece.v, 2), T.d[0] = __shfl_down_sync(0xffffffffu, piece.d[0], 2);
+    lnV = __shfl_sync(0xffffffffu, lnV, 21);
+    if (lane >= 21 || sub != 0) return;
+    const D lpn = piece;
+    const D Q = T + lpn;                                                   // -c log(m/mbhmax) + log_pl_norm + turn-on
+    const D A0 = (MREF < MBH_MIN) ? D(-INFINITY) : dlogaddexp(P, Q);       // :149-150
+    const D ln = -(A0 + log(MREF));                                        // :138
+    {
+        const int map5[5] = {0, 1, 3, 4, 5};
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (map5[q] == v) scal[S_LPN_D0 + q] = lpn.d[0];
+    }
+    scal[S_LN_D0 + v] = ln.d[0];
+    if (v != 0) return;
+    scal[S_LPN] = lpn.v;
+    scal[S_LOG_NORM] = ln.v;
+    scal[S_EXP_LPN] = exp(lpn.v);
+    scal[S_C2] = 2.0 * exp(lpn.v);
+    scal[S_LOG_C2] = LN2 + lpn.v;
+    scal[S_CONST] = 2.0 * ln.v + lnV - th[T_BETA] * LOG_MREF_PAIR;
 }
 
 // ---------------------------------------------------------------- packed mass records (last block of the prologue)
@@ -466,16 +481,14 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     else cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
     timeline_end(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
-    int bad = 0;
-    __syncthreads();   // pisn_row's thread-0 stores must be visible to the block before the re-read
-    if (!is_cos) {
-        if (threadIdx.x < 6) bad = !isfinite(__ldcg(aux + AUX_G + threadIdx.x * NM + row));
-    } else {
+    // (the PISN table is checked by the row block that finishes last, below)
+    if (is_cos) {
+        int bad = 0;
         const int k = blockIdx.x * PRO_THREADS + threadIdx.x;
-        for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));
+        for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));   // this thread's own stores
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
+        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
     // ---- the LAST ROW block (rows ticket): once all 256 PISN rows exist, the scalars (seven forward-mode chains of
     // ~1000 dependent FP64 instructions each: the longest serial piece of the prologue) and the packed mass records.
     // It does not wait for the cosmology cluster, which is still at work then (rows: ~5 us, cosmology: ~9.5 us).
@@ -488,17 +501,16 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
             __threadfence();
             timeline_begin(tl, TL_PRO_LAST);
             double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
-            for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) gtab[k] = __ldcg(aux + AUX_G + k);
-            __syncthreads();
+            int bad_g = 0;   // a non-finite PISN table (theta outside the prior support): flag it, finalize returns NaN
+            for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) {
+                const double g = __ldcg(aux + AUX_G + k);
+                gtab[k] = g;
+                bad_g |= !isfinite(g);
+            }
+            if (__syncthreads_or(bad_g) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
             if (threadIdx.x < 32) {
-                double* s_tmp = sm + 6 * NM;   // behind the table copy
-                if (threadIdx.x < 7) build_scalars(th, gtab, blob + OFF_SCAL, s_tmp, threadIdx.x);
-                else if (threadIdx.x < 9) build_scalars_extra(th, ec, blob + OFF_SCAL, s_tmp, threadIdx.x);
-                __syncwarp();
-                if (threadIdx.x == 0) {
-                    blob[OFF_SCAL + S_CONST] = 2.0 * s_tmp[0] + s_tmp[1] - th[T_BETA] * LOG_MREF_PAIR;
-                    flags[2] = 0u;   // re-arm the rows ticket
-                }
+                build_scalars(th, gtab, ec, blob + OFF_SCAL, threadIdx.x);
+                if (threadIdx.x == 0) flags[2] = 0u;   // re-arm the rows ticket
             } else {
                 pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
             }

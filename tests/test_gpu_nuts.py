@@ -81,7 +81,10 @@ def test_fit_driver_end_to_end_from_tables(tmp_path):
         assert post[k].shape == (2, 120, 128) and np.all(np.isfinite(post[k])), k
     assert np.allclose(post["neff"].min(axis=2), trace["det_neff_min"], rtol=1e-12)   # the same draws, re-evaluated
     h, om, w = (x[:, :, names.index(k)] for k in ("h", "Om", "w"))
-    assert np.allclose(post["hz"][:, :, 0], h) and np.all(np.diff(post["hz"], axis=2) > 0)   # hz(z=0) = h (:406)
+    from bumpcosmology_b200.intensity_models import coords
+    opz = 1 + coords["z_grid"]
+    hz = h[..., None] * np.sqrt(om[..., None] * opz ** 3 + (1 - om[..., None]) * opz ** (3 * (1 + w[..., None])))
+    assert np.allclose(post["hz"], hz, rtol=1e-12)                                          # h E(z) (:253-256, :406)
     # dNdVdt_fixed_mq at z = 0 is mref * R * exp(log_dN(mref, qref, zref)) = mref * R * exp(0 + ... ) (:404-405)
     assert np.all(post["dNdVdt_fixed_mq"][:, :, 0] > 0)
 
