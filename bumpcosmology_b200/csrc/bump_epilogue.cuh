@@ -374,8 +374,10 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         const int k = tid & 31, p = tid >> 5;
         static_assert(NFEAT + 3 <= 32 && EPI_THREADS == 256, "8 x 32 threads cover the slot columns");
         double s = 0.0;
-        if (k < NFEAT + 3)
+        if (k < NFEAT + 3) {
+#pragma unroll 4
             for (int b = p; b < nb_evt; b += EPI_THREADS / 32) s += __ldcg(slots + (size_t)b * EPI_SLOT + k);
+        }
         __syncthreads();   // `red` was last used by the block sums above
         red[32 + p * 32 + k] = s;
         __syncthreads();
@@ -392,10 +394,13 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     // L2 round trips (the serial tail was half of the epilogue's time at GWTC-3 size)
     __shared__ double s_part[P2P_MAX_RANKS * PARTIAL_LEN];
     __shared__ double s_out[OUT_HEADER];
+    __shared__ double s_sel[8 * EPI_SLOT];   // the injection blocks' (shift, sums): one load each, all in flight together
+    if (tid < nb_sel * EPI_SLOT) s_sel[tid] = __ldcg(slots + (size_t)nb_evt * EPI_SLOT + tid);
+    static_assert(8 * EPI_SLOT <= EPI_THREADS, "one thread per staged value");
+    __syncthreads();
     if (tid < P_SCAL0 + NSCAL) {
         double v = 0.0;
         if (tid < P_SCAL0) {
-            const double* ss = slots + (size_t)nb_evt * EPI_SLOT;
             if (tid == P_LLSUM) v = red[0];
             else if (tid == P_NOBS) v = (double)nobs;
             else if (tid >= P_FSUM0 && tid < P_FSUM0 + NFEAT) v = red[3 + tid - P_FSUM0];
@@ -404,16 +409,16 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
             else if (tid == P_SEL_M || (tid >= P_SEL_ACC0 && tid < P_SEL_ACC0 + NACC) || tid == P_NVALID_SEL) {
                 // rank-order merge of the injection blocks' (shift, sums): common shift, then a fixed-order sum
                 double M = -INFINITY;
-                for (int b = 0; b < nb_sel; ++b) M = fmax(M, __ldcg(ss + (size_t)b * EPI_SLOT));
+                for (int b = 0; b < nb_sel; ++b) M = fmax(M, s_sel[b * EPI_SLOT]);
                 if (tid == P_SEL_M) {
                     v = M;
                 } else {
                     const int k = (tid == P_NVALID_SEL) ? NACC : tid - P_SEL_ACC0;
                     for (int b = 0; b < nb_sel; ++b) {
-                        const double mb = __ldcg(ss + (size_t)b * EPI_SLOT);
+                        const double mb = s_sel[b * EPI_SLOT];
                         if (mb == -INFINITY) continue;
                         const double sc = (k == NACC) ? 1.0 : exp(mb - M);
-                        v += __ldcg(ss + (size_t)b * EPI_SLOT + 1 + k) * (k == 1 ? sc * sc : sc);
+                        v += s_sel[b * EPI_SLOT + 1 + k] * (k == 1 ? sc * sc : sc);
                     }
                 }
             }

@@ -183,8 +183,9 @@ __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo
     }
 }
 
-__device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts ec, double* __restrict__ aux,
-                                 double* __restrict__ blob, double* sm, const int chunk) {
+// Returns non-zero if one of this thread's table values is not finite (theta outside the prior support).
+__device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts ec, double* __restrict__ aux,
+                                double* __restrict__ blob, double* sm, const int chunk) {
     const int use_wa = ec.use_wa;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -318,6 +319,10 @@ __device__ void cosmology_tables(const double* __restrict__ th, const EvalConsts
         }
     }
     cluster.sync();   // no block may exit (and release its shared memory) while a peer still reads its knot
+    int bad = 0;
+#pragma unroll
+    for (int r = 1; r < COS_VALS; ++r) bad |= !isfinite(me[r]);
+    return bad;
 }
 
 // ---------------------------------------------------------------- scalars
@@ -477,15 +482,13 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     const bool is_cos = blockIdx.x < COS_CHUNKS;    // cosmology chunks first: they are the longer chains
     const int row = (int)blockIdx.x - COS_CHUNKS;
     timeline_begin(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
+    int bad = 0;
     if (!is_cos) pisn_row(th, row, aux, sm);
-    else cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
+    else bad = cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
     timeline_end(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     // (the PISN table is checked by the row block that finishes last, below)
     if (is_cos) {
-        int bad = 0;
-        const int k = blockIdx.x * PRO_THREADS + threadIdx.x;
-        for (int r = 1; r < 13; ++r) bad |= !isfinite(__ldcg(aux + AUX_ZG + r * NZ + k));   // this thread's own stores
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
         if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
     }
@@ -502,10 +505,16 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
             timeline_begin(tl, TL_PRO_LAST);
             double* gtab = sm;   // [6][NM] copy of the PISN table for the scalars
             int bad_g = 0;   // a non-finite PISN table (theta outside the prior support): flag it, finalize returns NaN
-            for (int k = threadIdx.x; k < 6 * NM; k += PRO_THREADS) {
-                const double g = __ldcg(aux + AUX_G + k);
-                gtab[k] = g;
-                bad_g |= !isfinite(g);
+            {   // all six loads of a thread in flight together: consumed one by one they cost six L2 round trips in a row
+                static_assert(6 * NM == 6 * PRO_THREADS, "six table values per thread");
+                double g[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) g[r] = __ldcg(aux + AUX_G + r * PRO_THREADS + threadIdx.x);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    gtab[r * PRO_THREADS + threadIdx.x] = g[r];
+                    bad_g |= !isfinite(g[r]);
+                }
             }
             if (__syncthreads_or(bad_g) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
             if (threadIdx.x < 32) {
