@@ -241,6 +241,7 @@ struct bump_ctx {
     bool slot_counted = false;
     bool slot_pinned = false;                // an evaluation of this context was captured into a caller's graph
     unsigned long long* d_timeline = nullptr;   // bump_debug_timeline
+    void *d_arena = nullptr, *d_plan_arena = nullptr;   // the small buffers live in two allocations
 };
 
 namespace {
@@ -252,10 +253,8 @@ int set_device(const bump_ctx* c) {
 
 void free_plan(bump_ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
-    cudaFree(c->d_rec_off), c->d_rec_off = nullptr;
-    cudaFree(c->d_part), c->d_part = nullptr;
-    cudaFree(c->d_slots), c->d_slots = nullptr;
-    cudaFree(c->d_out), c->d_out = nullptr;
+    cudaFree(c->d_plan_arena), c->d_plan_arena = nullptr;
+    c->d_rec_off = nullptr, c->d_part = nullptr, c->d_slots = nullptr, c->d_out = nullptr;
     if (c->h_out) cudaFreeHost(c->h_out), c->h_out = nullptr;
 }
 
@@ -345,16 +344,24 @@ int build_plan(bump_ctx* c) {
     c->lpe = 1;
     while (c->lpe < 32 && c->lpe < rpe) c->lpe *= 2;
     c->out_len = OUT_HEADER + c->evt.nrows;
-    CK(cudaMalloc(&c->d_rec_off, sizeof(int) * rec_off.size()));
-    CK(cudaMalloc(&c->d_part, sizeof(double) * PART_STRIDE * std::max(1, c->nrecords)));
+    const size_t b_rec = (sizeof(int) * rec_off.size() + 255) / 256 * 256;
+    const size_t b_part = (sizeof(double) * PART_STRIDE * std::max(1, c->nrecords) + 255) / 256 * 256;
     const int epb = EPI_THREADS / c->lpe;
     {   // injection blocks of the epilogue: one per 256 warps that own injection groups, at most 8
         const int64_t sel_groups = w.n_groups - w.n_evt_groups;
         const int64_t sel_warps = sel_groups > 0 ? (w.n_groups - 1) / w.gpw - w.n_evt_groups / w.gpw + 1 : 0;
         c->nb_sel = (int)std::min<int64_t>(8, std::max<int64_t>(1, (sel_warps + EPI_THREADS - 1) / EPI_THREADS));
     }
-    CK(cudaMalloc(&c->d_slots, sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + c->nb_sel)));
-    CK(cudaMalloc(&c->d_out, sizeof(double) * c->out_len));
+    const size_t b_slots = (sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + c->nb_sel) + 255) / 256 * 256;
+    const size_t b_out = (sizeof(double) * c->out_len + 255) / 256 * 256;
+    CK(cudaMalloc(&c->d_plan_arena, b_rec + b_part + b_slots + b_out));   // one allocation: see bump_ctx_create
+    {
+        char* base = static_cast<char*>(c->d_plan_arena);
+        c->d_out = reinterpret_cast<double*>(base);
+        c->d_slots = reinterpret_cast<double*>(base + b_out);
+        c->d_rec_off = reinterpret_cast<int*>(base + b_out + b_slots);
+        c->d_part = reinterpret_cast<double*>(base + b_out + b_slots + b_rec);
+    }
     CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
     CK(cudaMemcpy(c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size(), cudaMemcpyHostToDevice));
     c->plan_dirty = false;
@@ -552,25 +559,40 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     }
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&c->d_theta, sizeof(double) * NTHETA_MAX));
-    CK(cudaMemset(c->d_theta, 0, sizeof(double) * NTHETA_MAX));
-    CK(cudaMalloc(&c->d_aux, sizeof(double) * AUX_DOUBLES));
-    CK(cudaMalloc(&c->d_blob, BLOB_BYTES_MAX));
-    CK(cudaMemset(c->d_blob, 0, BLOB_BYTES_MAX));
+    {   // ONE allocation for the small per-context buffers: after an O5-size pass has swept the TLBs, the single-warp
+        // tails of the prologue and of the epilogue then miss on one page, not on one page per buffer
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            const size_t o = off;
+            off += (bytes + 255) / 256 * 256;
+            return o;
+        };
+        const size_t o_theta = take(sizeof(double) * NTHETA_MAX), o_aux = take(sizeof(double) * AUX_DOUBLES),
+                     o_blob = take(BLOB_BYTES_MAX), o_partial = take(sizeof(double) * PARTIAL_LEN),
+                     o_ticket = take(sizeof(unsigned int) * 8), o_fixed = take(sizeof(double) * NZ),
+                     o_epoch = take(2 * sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * 2 * TL_N);
+        CK(cudaMalloc(&c->d_arena, off));
+        CK(cudaMemset(c->d_arena, 0, off));
+        char* base = static_cast<char*>(c->d_arena);
+        c->d_theta = reinterpret_cast<double*>(base + o_theta);
+        c->d_aux = reinterpret_cast<double*>(base + o_aux);
+        c->d_blob = reinterpret_cast<double*>(base + o_blob);
+        c->d_partial = reinterpret_cast<double*>(base + o_partial);
+        c->d_ticket = reinterpret_cast<unsigned int*>(base + o_ticket);
+        c->d_fixed_tab = reinterpret_cast<double*>(base + o_fixed);
+        c->d_epoch = reinterpret_cast<unsigned long long*>(base + o_epoch);
+        c->d_timeline = reinterpret_cast<unsigned long long*>(base + o_tl);
+    }
     {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
         std::vector<double> expt(EXPT_DOUBLES);
         for (int j = 0; j < NEXPT; ++j)
             for (int r = 0; r < EXPT_REPL; ++r) expt[j * EXPT_REPL + r] = (double)exp2l((long double)j / NEXPT);
         CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * EXPT_DOUBLES, cudaMemcpyHostToDevice));
     }
-    CK(cudaMalloc(&c->d_partial, sizeof(double) * PARTIAL_LEN));
     // [0] unused, [1] epilogue ticket, [2] unused, [3] bad-input flag, [4] prologue ticket, [5] bad-theta flag
-    CK(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8));
-    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 8));
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    CK(cudaMalloc(&c->d_fixed_tab, sizeof(double) * NZ));
     if (device < 64) {   // the least-used constant-bank slot of this device that no captured graph has pinned
         std::lock_guard<std::mutex> lk(g_dev_mutex);
         int best = -1;
@@ -611,23 +633,17 @@ void bump_ctx_destroy(bump_ctx* c) {
         --g_slot_users[c->device * NSLOT + c->slot];
         if (c->slot_pinned) g_slot_pinned[c->device * NSLOT + c->slot] = false;
     }
-    cudaFree(c->d_timeline);
     free_plan(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
         if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
     cudaFree(c->d_mailbox);
+    cudaFree(c->d_arena);
+    cudaFree(c->d_plan_arena);
     cudaFree(c->d_peers);
-    cudaFree(c->d_epoch);
     cudaFree(c->evt.base);
     cudaFree(c->sel.base);
-    cudaFree(c->d_theta);
-    cudaFree(c->d_aux);
-    cudaFree(c->d_blob);
-    cudaFree(c->d_partial);
     cudaFree(c->d_gather);
-    cudaFree(c->d_ticket);
-    cudaFree(c->d_fixed_tab);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -762,7 +778,6 @@ int bump_p2p_export(bump_ctx* c, void* handle64) {
     if (!c->d_mailbox) {
         CK(cudaMalloc(&c->d_mailbox, sizeof(Mailbox)));
         CK(cudaMemset(c->d_mailbox, 0, sizeof(Mailbox)));
-        CK(cudaMalloc(&c->d_epoch, 2 * sizeof(unsigned long long)));
         CK(cudaMemset(c->d_epoch, 0, 2 * sizeof(unsigned long long)));
         CK(cudaDeviceSynchronize());
     }
@@ -911,7 +926,6 @@ int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 4 : 3) : 0
 int bump_debug_timeline(bump_ctx* c, const double* theta, double* out_us, int64_t out_len) {
     if (!theta || !out_us || out_len < 2 * TL_N) return fail(BUMP_E_INVALID, "bad timeline arguments");
     if (int r = ensure_ready(c)) return r;
-    if (!c->d_timeline) CK(cudaMalloc(&c->d_timeline, sizeof(unsigned long long) * 2 * TL_N));
     unsigned long long init[2 * TL_N], got[2 * TL_N];
     for (int k = 0; k < TL_N; ++k) init[2 * k] = ~0ull, init[2 * k + 1] = 0ull;
     const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
