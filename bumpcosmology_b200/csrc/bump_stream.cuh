@@ -495,8 +495,18 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
             if (more) {
                 p0 = (e_next == wk.nobs && k_next == 0) ? cols.sel_base + lane : p0 + BLOCK_DOUBLES;
                 hx = load_half(p0);
+                // the block after it is pulled towards L2 by ONE bulk prefetch carrying the same evict_first policy
+                // (per-line `prefetch.global.L2` has no such qualifier: its lines enter L2 at normal priority and an
+                // O5-size pass then still evicts everything else - measured: 11 us longer prologue + epilogue tails)
+#if defined(BUMP_L2_PREFETCH_PER_LINE)
                 if (lane < BLOCK_DOUBLES / 16)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
+#elif !defined(BUMP_NO_L2_PREFETCH)
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p0 + BLOCK_DOUBLES),
+                                 "n"(BLOCK_DOUBLES * 8), "l"(l2_stream_policy)
+                                 : "memory");
+#endif
             }
         };
         if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(USC_ARG hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
