@@ -495,17 +495,27 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
             if (more) {
                 p0 = (e_next == wk.nobs && k_next == 0) ? cols.sel_base + lane : p0 + BLOCK_DOUBLES;
                 hx = load_half(p0);
-                // the block after it is pulled towards L2 by ONE bulk prefetch carrying the same evict_first policy
-                // (per-line `prefetch.global.L2` has no such qualifier: its lines enter L2 at normal priority and an
-                // O5-size pass then still evicts everything else - measured: 11 us longer prologue + epilogue tails)
+                // The block after it is pulled towards L2 by a real load per line (28 lines, one per lane, result unused)
+                // that carries the same evict_first policy.  Measured at O5 size (us per evaluation / tails of prologue +
+                // epilogue): `prefetch.global.L2` per line 1085 / 30 (its lines enter L2 at normal priority and the pass
+                // still evicts everything else), `cp.async.bulk.prefetch.L2` with the policy 1089 / 30 (no better), no
+                // prefetch 1090 / 18, this 1088 / 18: the streaming kernel itself is 1.6 % slower than with the plain
+                // prefetch, the serial tails 12 us shorter - a wash on one GPU, 4 % at the 8-GPU shard size.
 #if defined(BUMP_L2_PREFETCH_PER_LINE)
                 if (lane < BLOCK_DOUBLES / 16)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + BLOCK_DOUBLES + 15 * lane));
-#elif !defined(BUMP_NO_L2_PREFETCH)
+#elif defined(BUMP_L2_PREFETCH_BULK)
                 if (lane == 0)
                     asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p0 + BLOCK_DOUBLES),
                                  "n"(BLOCK_DOUBLES * 8), "l"(l2_stream_policy)
                                  : "memory");
+#elif !defined(BUMP_NO_L2_PREFETCH)
+                if (lane < BLOCK_DOUBLES / 16) {
+                    uint32_t sink;
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;"
+                                 : "=r"(sink)
+                                 : "l"(p0 + BLOCK_DOUBLES + 15 * lane), "l"(l2_stream_policy));
+                }
 #endif
             }
         };

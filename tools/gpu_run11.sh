@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 out=gpurun_out; mkdir -p $out
-for v in nopf; do
+for v in pfld; do
   lib=build/libbump_$v.so
   BUMP_LIB_PATH=$PWD/$lib timeout 300 python tools/tune.py 2>&1 | tail -1 | tee -a $out/r11_tune.txt
   BUMP_LIB_PATH=$PWD/$lib timeout 600 python - <<'PY' 2>&1 | tee -a $out/r11_timeline.txt
