@@ -136,12 +136,12 @@ struct Peers {
 // Called by all threads of ONE block.  Returns STATUS_OK, STATUS_EXCHANGE_TIMEOUT (a peer never arrived) or
 // STATUS_EXCHANGE_POISONED (a peer failed, now or earlier).
 __device__ inline double p2p_exchange(const Peers& peers, const double* __restrict__ partial,
-                                      unsigned long long* __restrict__ state) {
+                                      unsigned long long* __restrict__ state, int& par /* out: parity of this exchange */) {
     __shared__ int s_status;
     const int tid = threadIdx.x;
     const unsigned long long epoch = state[0] + 1ull;
     const bool broken = state[1] != 0ull;
-    const int par = (int)(epoch & 1ull);
+    par = (int)(epoch & 1ull);
     if (tid == 0) s_status = broken ? 2 : 0;
     if (!broken)
         for (int r = 0; r < peers.nranks; ++r)
@@ -437,10 +437,10 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         if (peers) {   // multi-rank, fused exchange over peer memory
             __threadfence();
             __syncthreads();
-            status = p2p_exchange(*peers, s_part, exchange_state);   // pushes the shared-memory copy to every peer
+            int par;   // (not re-read from exchange_state: only thread 0 has written the new epoch there)
+            status = p2p_exchange(*peers, s_part, exchange_state, par);   // pushes the shared-memory copy to every peer
             if (status == STATUS_OK) {
                 nparts = peers->nranks;
-                const int par = (int)(exchange_state[0] & 1ull);
                 const double* mail = &peers->box[peers->rank]->mail[par][0][0];
                 for (int k = tid; k < nparts * PARTIAL_LEN; k += EPI_THREADS) s_part[k] = __ldcg(mail + k);
             }

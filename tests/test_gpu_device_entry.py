@@ -148,3 +148,26 @@ def test_capture_is_refused_when_the_constant_slot_is_shared(small):
         assert np.array_equal(like.raw(_thetas()[0]), ref, equal_nan=True)
     for like in likes:
         like.close()
+
+
+def test_peer_memory_exchange_path_with_a_single_rank(small):
+    """The fused exchange code path (partial -> mailbox -> flags -> merge from the mailbox) with one rank attached to
+    its own mailbox: no kernel waits for another launch, so it may run on one GPU.  Must equal the plain evaluation
+    bit for bit, from the first evaluation on, and report status 0."""
+    import ctypes as C
+    from bumpcosmology_b200 import _lib
+    from bumpcosmology_b200.likelihood import Hyperlikelihood
+    plain = Hyperlikelihood(*small.as_args())
+    like = Hyperlikelihood(*small.as_args())
+    raw = (C.c_char * 64)()
+    _lib.check(like.lib.bump_p2p_export(like._ctx, raw))
+    _lib.check(like.lib.bump_p2p_set_timeout(like._ctx, 2.0))
+    _lib.check(like.lib.bump_p2p_attach(like._ctx, raw, 1, 0))
+    for th in _thetas():
+        a, b = like.raw(th).copy(), plain.raw(th).copy()
+        assert a[_lib.OUT_STATUS] == 0.0
+        assert np.array_equal(a, b, equal_nan=True), np.flatnonzero(a != b)[:10]
+    _lib.check(like.lib.bump_p2p_detach(like._ctx))
+    assert np.array_equal(like.raw(_thetas()[0]), plain.raw(_thetas()[0]), equal_nan=True)
+    like.close()
+    plain.close()
