@@ -440,14 +440,17 @@ def main():
     # ---- N > 1: the sharded result against an unsharded evaluation of the whole catalog on rank 0's GPU
     result_check = None
     if world > 1:
-        res_sh = like(THETA_DEFAULT)
+        # at a theta that differs from the one of the evaluation before it: a stale partial from the previous exchange
+        # (same theta in the timed loops) would otherwise go unnoticed
+        like(thetas[2])
+        res_sh = like(thetas[1])
         neff_parts = [None] * world
         dist.all_gather_object(neff_parts, res_sh.neff)
         flat_sh = _flat(res_sh)
         ok = torch.ones(1, device="cuda")
         if rank == 0:
             full = Hyperlikelihood(*cat.as_args(), device=local_rank, wa=args.wa)
-            r1 = full(THETA_DEFAULT)
+            r1 = full(thetas[1])
             full.close()
             f1 = _flat(r1)
             gs = max(1.0, float(np.max(np.abs(r1.dloglike))))
