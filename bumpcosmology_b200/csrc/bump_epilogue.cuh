@@ -226,8 +226,7 @@ __device__ __forceinline__ void epi_block_sum(double (&v)[NV], double* red) {
 }
 
 // part: [nrecords][PART_STRIDE] written by the streaming kernel; event e (groups [e*g_evt, (e+1)*g_evt)) is covered
-// by warps floor(e*g_evt/gpw_evt) .. floor(((e+1)*g_evt-1)/gpw_evt), merged here in that fixed order; every warp
-// with injection groups also holds one injection record (its last).
+// by warps floor(e*g_evt/gpw) .. floor(((e+1)*g_evt-1)/gpw), merged here in that fixed order.
 //   blocks 0 .. nb_evt-1 : one thread per event -> logsumexp, Neff, normalised features; block sum -> slot[b]
 //   blocks nb_evt .. nb_evt+nb_sel-1 : a slice of the injection records each -> (shift, sums) in slot[b]
 //   last block to finish : fixed-order sum of the slots -> this rank's partial; with `out_header` non-null
@@ -251,11 +250,11 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     const int nb_evt = (nobs + epb - 1) / epb;
     double* slot = slots + (size_t)blockIdx.x * EPI_SLOT;
     // 32-bit group arithmetic (n_groups < 2^31 is checked on the host; 64-bit divisions are emulated and slow)
-    const int g_evt = (int)wk.g_evt, gpw = (int)wk.gpw_evt, gpw_sel = (int)wk.gpw_sel, n_sel_groups = (int)wk.n_sel_groups;
-    auto rec_index = [&](const int w, const int e) {   // warp w's records start at rec_off[w]: its events in order ...
-        return rec_off[w] + (e - (w * gpw) / g_evt);
+    const int g_evt = (int)wk.g_evt, gpw = (int)wk.gpw, n_evt_groups = (int)wk.n_evt_groups, n_groups = (int)wk.n_groups;
+    auto rec_index = [&](const int w, const int e) {   // warp w's records start at rec_off[w], ordered by event
+        const int g0 = w * gpw;
+        return rec_off[w] + (e - (g0 < n_evt_groups ? g0 / g_evt : nobs));
     };
-    auto sel_index = [&](const int w) { return rec_off[w + 1] - 1; };   // ... then its injection record, the last one
     if ((int)blockIdx.x < nb_evt) {
         // ---- events
         double ev[NFEAT + 3];   // llsum, nvalid, ndead, phi[NFEAT]
@@ -318,14 +317,15 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         // ---- injections (pseudo-event nobs): global shift first, then plain sums over the warps owning its groups
         // (the warps that own injection groups are split evenly over the nb_sel injection blocks: one block was the
         // longest-running of the kernel at GWTC-3 size)
-        const int wa0 = 0;                                             // warps 0 .. wa1 own injection groups
-        const int wa1 = (n_sel_groups + gpw_sel - 1) / gpw_sel - 1;
+        const bool has_sel = n_groups > n_evt_groups;
+        const int wa0 = has_sel ? n_evt_groups / gpw : 0;
+        const int wa1 = has_sel ? (n_groups - 1) / gpw : -1;
         const int per = (wa1 - wa0 + nb_sel) / nb_sel;                 // ceil((wa1 - wa0 + 1) / nb_sel)
         const int ws0 = wa0 + ((int)blockIdx.x - nb_evt) * per;
         const int ws1 = min(wa1, ws0 + per - 1);
         double mx = -INFINITY;
         for (int w = ws0 + tid; w <= ws1; w += EPI_THREADS)
-            mx = fmax(mx, part[(size_t)sel_index(w) * PART_STRIDE]);
+            mx = fmax(mx, part[(size_t)rec_index(w, nobs) * PART_STRIDE]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((tid & 31) == 0) red[tid >> 5] = mx;
@@ -341,7 +341,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
 #pragma unroll
         for (int k = 0; k <= NACC; ++k) sv[k] = 0.0;
         for (int w = ws0 + tid; w <= ws1; w += EPI_THREADS) {
-            const double* p = part + (size_t)sel_index(w) * PART_STRIDE;
+            const double* p = part + (size_t)rec_index(w, nobs) * PART_STRIDE;
             if (p[0] == -INFINITY) continue;
             const double s = exp(p[0] - mx);
             sv[0] += p[1] * s;

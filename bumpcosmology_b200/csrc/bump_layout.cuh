@@ -122,24 +122,24 @@ constexpr int NACC = 2 + NFEAT;   // S, S2, features
 constexpr int PART_STRIDE = 24;   // per-record partial: [0] shift m, [1..19] acc, [20] nvalid
 
 // ---- work decomposition of the streaming kernel: the unit is a GROUP of 64 consecutive samples of one event
-// (or of the injection set), two samples per lane.  Every warp of the grid owns TWO contiguous ranges: an equal share
-// of the event groups and an equal share of the injection groups, so that all warps carry the same mix of work (the
-// injection set, sorted as one long event, hits far fewer distinct table bins per warp and runs faster per group: with
-// one range per warp the warps that held injection groups finished 8 % earlier than the others, round 2).  A warp
-// writes one RECORD per event it touches and one for its injection range; events never need a block-wide reduction and
-// no warp waits for another.
+// (or of the injection set), two samples per lane.  Groups are numbered events-first; every warp of the grid owns
+// one contiguous, equally long range of groups and writes one RECORD per event it touches (plus one for the
+// injection set), so events never need a block-wide reduction and no warp waits for another.
 constexpr int GROUP = 64;
 struct Work {
     int64_t g_evt;         // groups per event  = ceil(evt_stride / GROUP)
     int64_t n_evt_groups;  // nobs * g_evt
-    int64_t n_sel_groups;  // groups of the injection set
-    int64_t gpw_evt;       // event groups per warp     (warp w: [w gpw_evt, (w+1) gpw_evt) clipped; may be empty)
-    int64_t gpw_sel;       // injection groups per warp (warp w: [w gpw_sel, (w+1) gpw_sel) clipped; may be empty)
+    int64_t n_groups;      // + groups of the injection set
+    int64_t gpw;           // groups per warp (last warps may own fewer / none)
     int64_t evt_stride;    // padded samples per event (multiple of GROUP: the kernel loads whole groups unpredicated)
     int64_t sel_stride;    // padded injections (multiple of GROUP)
     int32_t nobs;
-    int32_t nwarps;        // warps with at least one group
+    int32_t nwarps;
 };
+// event id of a group (the injection set is pseudo-event `nobs`)
+__host__ __device__ inline int64_t group_event(const Work& w, const int64_t g) {
+    return g < w.n_evt_groups ? g / w.g_evt : (int64_t)w.nobs;
+}
 
 constexpr int NCOL = 7;  // dl, m1det, q, log m1det, log q, log1p q, log pdraw
 enum Col { C_DL = 0, C_M1D, C_Q, C_LM, C_LQ, C_L1Q, C_LPD };
@@ -190,7 +190,6 @@ enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE,
                     TL_STREAM_STAGED, // streaming kernel: first .. last CTA past the table staging
                     TL_EPI_BLOCKS,    // epilogue: per-event / injection phase of all blocks
                     TL_EPI_LAST,      // epilogue: the last block's tail (slot sums, partial, exchange, finalize)
-                    TL_STREAM_WARPS,  // streaming kernel: the first .. the last warp to finish its range of groups
                     TL_N };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long global_ns() {

@@ -323,27 +323,24 @@ int build_plan(bump_ctx* c) {
     w.sel_stride = c->sel.nrows ? c->sel.stride : 0;
     w.g_evt = std::max<int64_t>(1, (w.evt_stride + GROUP - 1) / GROUP);
     w.n_evt_groups = w.nobs * w.g_evt;
-    w.n_sel_groups = (w.sel_stride + GROUP - 1) / GROUP;
-    if (w.n_evt_groups + w.n_sel_groups >= (int64_t(1) << 31))
+    w.n_groups = w.n_evt_groups + (w.sel_stride + GROUP - 1) / GROUP;
+    if (w.n_groups >= (int64_t(1) << 31))
         return fail(BUMP_E_INVALID, "shard too large: more than 2^31 groups of 64 samples on one rank");
-    // one CTA per SM (persistent); every warp gets an equal share of the event groups AND of the injection groups
+    // one CTA per SM (persistent); use fewer CTAs only when there are fewer groups than warps
     const int64_t max_warps = (int64_t)c->sm_count * STREAM_WARPS;
-    auto per_warp = [&](const int64_t n) { return std::max<int64_t>(1, (n + max_warps - 1) / max_warps); };
-    w.gpw_evt = per_warp(w.n_evt_groups);
-    w.gpw_sel = per_warp(w.n_sel_groups);
-    const int64_t we = (w.n_evt_groups + w.gpw_evt - 1) / w.gpw_evt, ws = (w.n_sel_groups + w.gpw_sel - 1) / w.gpw_sel;
-    w.nwarps = (int32_t)std::max<int64_t>(1, std::max(we, ws));
+    if (const char* e = getenv("BUMP_GPW")) w.gpw = std::max<int64_t>(1, atoll(e));
+    else w.gpw = std::max<int64_t>(1, (w.n_groups + max_warps - 1) / max_warps);
+    w.nwarps = (int32_t)std::max<int64_t>(1, (w.n_groups + w.gpw - 1) / w.gpw);
     c->grid = (w.nwarps + STREAM_WARPS - 1) / STREAM_WARPS;
     std::vector<int> rec_off(w.nwarps + 1, 0);
-    for (int i = 0; i < w.nwarps; ++i) {   // records of warp i: one per event its event range touches, then its injection record
-        const int64_t g0 = std::min((int64_t)i * w.gpw_evt, w.n_evt_groups), g1 = std::min(g0 + w.gpw_evt, w.n_evt_groups);
-        const int64_t s0 = std::min((int64_t)i * w.gpw_sel, w.n_sel_groups), s1 = std::min(s0 + w.gpw_sel, w.n_sel_groups);
-        const int n = (g0 < g1 ? (int)((g1 - 1) / w.g_evt - g0 / w.g_evt + 1) : 0) + (s0 < s1 ? 1 : 0);
+    for (int i = 0; i < w.nwarps; ++i) {
+        const int64_t g0 = (int64_t)i * w.gpw, g1 = std::min(g0 + w.gpw, w.n_groups);
+        const int n = g0 < g1 ? (int)(group_event(w, g1 - 1) - group_event(w, g0) + 1) : 0;
         rec_off[i + 1] = rec_off[i] + n;
     }
     c->nrecords = rec_off[w.nwarps];
     // epilogue: lanes per event = records per event rounded up to a power of two (<= 32)
-    const int64_t rpe = (w.g_evt + w.gpw_evt - 1) / w.gpw_evt + 1;
+    const int64_t rpe = (w.g_evt + w.gpw - 1) / w.gpw + 1;
     c->lpe = 1;
     while (c->lpe < 32 && c->lpe < rpe) c->lpe *= 2;
     c->out_len = OUT_HEADER + c->evt.nrows;
@@ -351,7 +348,8 @@ int build_plan(bump_ctx* c) {
     const size_t b_part = (sizeof(double) * PART_STRIDE * std::max(1, c->nrecords) + 255) / 256 * 256;
     const int epb = EPI_THREADS / c->lpe;
     {   // injection blocks of the epilogue: one per 256 warps that own injection groups, at most 8
-        const int64_t sel_warps = (w.n_sel_groups + w.gpw_sel - 1) / w.gpw_sel;
+        const int64_t sel_groups = w.n_groups - w.n_evt_groups;
+        const int64_t sel_warps = sel_groups > 0 ? (w.n_groups - 1) / w.gpw - w.n_evt_groups / w.gpw + 1 : 0;
         c->nb_sel = (int)std::min<int64_t>(8, std::max<int64_t>(1, (sel_warps + EPI_THREADS - 1) / EPI_THREADS));
     }
     const size_t b_slots = (sizeof(double) * EPI_SLOT * ((w.nobs + epb - 1) / epb + c->nb_sel) + 255) / 256 * 256;
@@ -413,7 +411,7 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
                                sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
 #endif
     if (k0) cudaEventRecord(k0, s);
-    if (c->work.n_evt_groups + c->work.n_sel_groups > 0)
+    if (c->work.n_groups > 0)
         stream_kernel_for(c)<<<c->grid, STREAM_THREADS, stream_smem_bytes(c->use_wa, c->fixed), s>>>(
             columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part, tl);
     if (k1) cudaEventRecord(k1, s);
@@ -975,8 +973,8 @@ int bump_debug_timeline(bump_ctx* c, const double* theta, double* out_us, int64_
 int bump_plan_info(bump_ctx* c, int64_t* info8) {
     if (!info8) return fail(BUMP_E_INVALID, "null info");
     if (int r = ensure_ready(c)) return r;
-    info8[0] = c->work.n_evt_groups + c->work.n_sel_groups;
-    info8[1] = c->work.gpw_evt + c->work.gpw_sel;
+    info8[0] = c->work.n_groups;
+    info8[1] = c->work.gpw;
     info8[2] = c->nrecords;
     info8[3] = c->grid;
     info8[4] = STREAM_THREADS;

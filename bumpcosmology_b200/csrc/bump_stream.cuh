@@ -425,19 +425,17 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     const int warp = blockIdx.x * STREAM_WARPS + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 #endif
     if (warp >= wk.nwarps) return;
-    // this warp's two ranges: event groups [ge0, ge1) and injection groups [gs0, gs1), walked one after the other.
-    // 32-bit group arithmetic (the group count < 2^31 is checked on the host); 64-bit only to form addresses
-    const int n_evt_groups = (int)wk.n_evt_groups, n_sel_groups = (int)wk.n_sel_groups, g_evt = (int)wk.g_evt;
-    const int ge0 = min(warp * (int)wk.gpw_evt, n_evt_groups), ge1 = min(ge0 + (int)wk.gpw_evt, n_evt_groups);
-    const int gs0 = min(warp * (int)wk.gpw_sel, n_sel_groups), gs1 = min(gs0 + (int)wk.gpw_sel, n_sel_groups);
-    const int n_evt = ge1 - ge0, n_tot = n_evt + (gs1 - gs0);
-    if (n_tot == 0) return;
-    const int e_first = n_evt > 0 ? ge0 / g_evt : wk.nobs;
-    double* rec = part + (size_t)rec_off[warp] * PART_STRIDE;   // one record per event touched, then the injection record
+    // 32-bit group arithmetic (n_groups < 2^31 is checked on the host); 64-bit only to form addresses
+    const int n_groups = (int)wk.n_groups, n_evt_groups = (int)wk.n_evt_groups, g_evt = (int)wk.g_evt;
+    const int g0 = warp * (int)wk.gpw;
+    const int g1 = min(g0 + (int)wk.gpw, n_groups);
+    if (g0 >= g1) return;
+    const int e_first = g0 < n_evt_groups ? g0 / g_evt : wk.nobs;
+    double* rec = part + (size_t)rec_off[warp] * PART_STRIDE;
 
-    // position of the first group: event e (the injection set is pseudo-event nobs), group-in-event k
+    // position of group g0: event e, group-in-event k
     int e = e_first;
-    int k = n_evt > 0 ? ge0 - e * g_evt : 0;
+    int k = (e < wk.nobs) ? g0 - e * g_evt : g0 - n_evt_groups;
     ThreadAcc A;
     acc_init(A);
     // The loads are software-pipelined at half-group granularity - y(g) is issued before x(g) is evaluated, x(g+1)
@@ -446,10 +444,12 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     struct Half {
         double dl, m1, q, lm, lq, l1q, lpd;
     };
-    // event group g lives in block g of the events buffer, injection group g in block g of the injection buffer: the
-    // pointer advances by one block per group and is re-based once, where the warp passes from its event range to its
-    // injection range
-    const double* const sel_start = cols.sel_base + (int64_t)gs0 * BLOCK_DOUBLES + lane;
+    // group g of the kernel's numbering lives in block g of the events buffer, or block g - n_evt_groups of the
+    // injection buffer: the pointer advances by one block per group and is re-based once, at the set boundary
+    auto block_of = [&](const int ee, const int kk) {
+        return (ee >= wk.nobs ? cols.sel_base + (int64_t)kk * BLOCK_DOUBLES
+                              : cols.evt_base + ((int64_t)ee * g_evt + kk) * BLOCK_DOUBLES) + lane;
+    };
     auto load_half = [&](const double* p) {   // p = block + lane (x half) or block + 32 + lane (y half)
         // volatile: keeps the load where it is written (ptxas otherwise sinks it to its first use to save
         // registers, which exposes the full L2 latency once per group)
@@ -476,9 +476,9 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         h.lpd = ld(p + C_LPD * GROUP);
         return h;
     };
-    const double* p0 = n_evt > 0 ? cols.evt_base + (int64_t)ge0 * BLOCK_DOUBLES + lane : sel_start;
+    const double* p0 = block_of(e, k);
     Half hx = load_half(p0);
-    for (int i = 0; i < n_tot; ++i) {
+    for (int g = g0; g < g1; ++g) {
         const Half hy = load_half(p0 + 32);
         auto nothing = [] {};
         if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(USC_ARG hx.dl, hx.m1, hx.q, hx.lm, hx.lq, hx.l1q, hx.lpd, sb, rep, A, nothing);
@@ -486,17 +486,14 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         // ---- advance to the next group; its x half is issued from inside the y evaluation (after y's inputs are
         // consumed), and the block after it is pulled towards L2 (28 lines: one per lane)
         int e_next = e, k_next = k + 1;
-        const bool to_sel = (i + 1 == n_evt);       // the next group is the first of the injection range
-        if (to_sel) {
-            e_next = wk.nobs;
-        } else if (i + 1 < n_evt && k_next == g_evt) {
+        if (k_next == ((e < wk.nobs) ? g_evt : n_groups - n_evt_groups)) {
             k_next = 0;
             e_next = e + 1;
         }
-        const bool more = i + 1 < n_tot;
+        const bool more = g + 1 < g1;
         auto next_loads = [&] {
             if (more) {
-                p0 = to_sel ? sel_start : p0 + BLOCK_DOUBLES;
+                p0 = (e_next == wk.nobs && k_next == 0) ? cols.sel_base + lane : p0 + BLOCK_DOUBLES;
                 hx = load_half(p0);
                 // The block after it is pulled towards L2 by a real load per line (28 lines, one per lane, result unused)
                 // that carries the same evict_first policy.  Measured at O5 size (us per evaluation / tails of prologue +
@@ -524,22 +521,14 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         };
         if constexpr (FIXED) eval_sample_fixed<SLOT, WA>(USC_ARG hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
         else eval_sample<SLOT, WA>(USC_ARG hy.dl, hy.m1, hy.q, hy.lm, hy.lq, hy.l1q, hy.lpd, sb, rep, A, next_loads);
-        if (!more || e_next != e) {   // event (or injection range) complete for this warp: one record
-            // events e_first .. : records 0 .. ; the injection record follows the event records (index n_evt > 0 ?
-            // last event - e_first + 1 : 0, which is exactly nobs - e_first clipped to the events this warp touched)
-            const int ri = (e < wk.nobs) ? e - e_first : (n_evt > 0 ? (ge1 - 1) / g_evt - e_first + 1 : 0);
-            warp_flush(A, rec + (size_t)ri * PART_STRIDE);
+        if (!more || e_next != e) {   // event complete (for this warp): one record
+            warp_flush(A, rec + (size_t)(e - e_first) * PART_STRIDE);
             acc_init(A);
         }
         e = e_next;
         k = k_next;
     }
-    if (tl != nullptr && lane == 0) {   // every warp: they finish apart
-        const unsigned long long t = global_ns();
-        atomicMax(tl + 2 * TL_STREAM + 1, t);
-        atomicMin(tl + 2 * TL_STREAM_WARPS, t);
-        atomicMax(tl + 2 * TL_STREAM_WARPS + 1, t);
-    }
+    if (tl != nullptr && lane == 0) atomicMax(tl + 2 * TL_STREAM + 1, global_ns());   // every warp: they finish apart
 }
 
 #undef K_SC
