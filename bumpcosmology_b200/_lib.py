@@ -44,6 +44,7 @@ SIGNATURES = {
     "bump_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "bump_p2p_detach": (C.c_int, [C.c_void_p]),
     "bump_p2p_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
+    "bump_debug_warp_times": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "bump_debug_timeline": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64]),
     "bump_debug_tables": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64]),
     "bump_debug_math": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]),

@@ -190,7 +190,9 @@ enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE,
                     TL_STREAM_STAGED, // streaming kernel: first .. last CTA past the table staging
                     TL_EPI_BLOCKS,    // epilogue: per-event / injection phase of all blocks
                     TL_EPI_LAST,      // epilogue: the last block's tail (slot sums, partial, exchange, finalize)
+                    TL_STREAM_WARPS,  // streaming kernel: the first .. the last warp to finish its range of groups
                     TL_N };
+constexpr int TL_WARP_SLOTS = 4096;   // per-warp end times of the streaming kernel behind the phase slots
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;

@@ -570,7 +570,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         const size_t o_theta = take(sizeof(double) * NTHETA_MAX), o_aux = take(sizeof(double) * AUX_DOUBLES),
                      o_blob = take(BLOB_BYTES_MAX), o_partial = take(sizeof(double) * PARTIAL_LEN),
                      o_ticket = take(sizeof(unsigned int) * 8), o_fixed = take(sizeof(double) * NZ),
-                     o_epoch = take(2 * sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * 2 * TL_N);
+                     o_epoch = take(2 * sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * (2 * TL_N + TL_WARP_SLOTS));
         CK(cudaMalloc(&c->d_arena, off));
         CK(cudaMemset(c->d_arena, 0, off));
         char* base = static_cast<char*>(c->d_arena);
@@ -922,6 +922,17 @@ int bump_ctx_flags(const bump_ctx* c) { return c ? (int)c->flags : -1; }
 int bump_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }   // for bump_nuts.cpp
 
 int bump_launches_per_eval(const bump_ctx* c) { return c ? (c->comm ? 4 : 3) : 0; }
+
+int bump_debug_warp_times(bump_ctx* c, double* out_us, int64_t nwarps) {
+    if (!c || !out_us || nwarps < 1 || nwarps > TL_WARP_SLOTS) return fail(BUMP_E_INVALID, "bad warp-times arguments");
+    if (int r = set_device(c)) return r;
+    std::vector<unsigned long long> t(2 * TL_N + nwarps);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(t.data(), c->d_timeline, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+    const unsigned long long t0 = t[2 * TL_STREAM];
+    for (int64_t w = 0; w < nwarps; ++w) out_us[w] = t[2 * TL_N + w] ? (double)(t[2 * TL_N + w] - t0) * 1e-3 : -1.0;
+    return BUMP_OK;
+}
 
 int bump_debug_timeline(bump_ctx* c, const double* theta, double* out_us, int64_t out_len) {
     if (!theta || !out_us || out_len < 2 * TL_N) return fail(BUMP_E_INVALID, "bad timeline arguments");

@@ -528,7 +528,13 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         e = e_next;
         k = k_next;
     }
-    if (tl != nullptr && lane == 0) atomicMax(tl + 2 * TL_STREAM + 1, global_ns());   // every warp: they finish apart
+    if (tl != nullptr && lane == 0) {   // every warp: they finish apart
+        const unsigned long long t = global_ns();
+        atomicMax(tl + 2 * TL_STREAM + 1, t);
+        atomicMin(tl + 2 * TL_STREAM_WARPS, t);
+        atomicMax(tl + 2 * TL_STREAM_WARPS + 1, t);
+        if (warp < TL_WARP_SLOTS) tl[2 * TL_N + warp] = t;   // bump_debug_warp_times
+    }
 }
 
 #undef K_SC

@@ -200,7 +200,7 @@ class Hyperlikelihood:
         GPU's global timer, relative to the first kernel's first block."""
         th = self._set_theta(theta)
         names = ("prologue", "stream", "epilogue", "finalize", "prologue.rows", "prologue.cosmology", "prologue.last_block",
-                 "stream.staged", "epilogue.blocks", "epilogue.last_block")
+                 "stream.staged", "epilogue.blocks", "epilogue.last_block", "stream.warps_done")
         buf = np.empty(2 * len(names))
         _lib.check(self.lib.bump_debug_timeline(self._ctx, _lib.as_dp(th), _lib.as_dp(buf), buf.shape[0]))
         return {n: (float(buf[2 * i]), float(buf[2 * i + 1])) for i, n in enumerate(names) if buf[2 * i + 1] >= 0}

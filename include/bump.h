@@ -162,10 +162,14 @@ int bump_time_evals(bump_ctx* ctx, const double* theta, int iters, float* total_
 /* Per-kernel timeline of ONE evaluation launched directly (no graph): out_us[2k], out_us[2k+1] = start of the first
  * block / end of the last block of phase k (0 prologue, 1 streaming, 2 epilogue, 3 finalize, then sub-phases:
  * 4 prologue PISN rows, 5 prologue cosmology blocks, 6 prologue last block, 7 streaming kernel past the table staging,
- * 8 epilogue per-event phase, 9 epilogue last block; -1 if it did not run)
+ * 8 epilogue per-event phase, 9 epilogue last block, 10 first / last warp of the streaming kernel to finish;
+ * -1 if it did not run)
  * in microseconds on the GPU's global timer, relative to the start of the first kernel; launched as one CUDA graph
- * like a normal evaluation (directly with BUMP_FLAG_NO_GRAPH).  out_len >= 20. */
+ * like a normal evaluation (directly with BUMP_FLAG_NO_GRAPH).  out_len >= 22. */
 int bump_debug_timeline(bump_ctx* ctx, const double* theta, double* out_us, int64_t out_len);
+/* After bump_debug_timeline: when each of the first nwarps (<= 4096) warps of the streaming kernel finished, in
+ * microseconds from the kernel's start (-1: the warp had no work).  Shows the load balance of the static plan. */
+int bump_debug_warp_times(bump_ctx* ctx, double* out_us, int64_t nwarps);
 
 /* Number of kernel launches one bump_eval performs (for bench.py's gpu_launches). */
 int bump_launches_per_eval(const bump_ctx* ctx);
