@@ -25,6 +25,8 @@ constexpr double LN2 = 0.69314718055994530942;
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;     // log(sqrt(2 pi))
 constexpr double FOUR_PI = 12.566370614359172954;
 
+constexpr double MASS_BEYOND_LOG = -5.0e4;   // log dN of the mass table's beyond-the-grid record (exp saturates: ~0)
+
 constexpr int NTHETA = 14;
 constexpr int NTHETA_MAX = 15;
 enum ThetaIdx { T_H = 0, T_OM, T_W, T_A, T_B, T_C, T_MPISN, T_MBHMAX, T_SIGMA, T_FPL, T_BETA, T_LAM, T_KAPPA,

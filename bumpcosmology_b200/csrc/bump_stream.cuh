@@ -38,6 +38,7 @@ constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 __host__ __device__ constexpr int stream_smem_bytes(const bool wa, const bool fixed) {
     return blob_doubles(wa, fixed) * 8;
 }
+constexpr double ZERO_WEIGHT_SHIFT = -5.0e4;   // exponent shift of a sample without weight: exp saturates (~1e-304)
 constexpr double RESCALE_GAP = 200.0;   // p <= e^200 * O(e^50): p^2 stays far below DBL_MAX
 
 // The theta-dependent scalars of the current evaluation, copied device-to-device from the table blob right before
@@ -142,12 +143,11 @@ __device__ __forceinline__ void mass_eval(USC_PARAM const double m, const double
     const double pos = fma(m, K_SC[S_INV_DMBH], K_SC[S_POS0]);
     o.pos = pos;
     int b = __double2int_rd(pos);
-    b = min(max(b, 0), NM - 2);
+    b = min(max(b, 0), NM - 1);                   // NM-1: the beyond-the-grid record (log dN = -5e4, slope 0; :145)
     o.u = pos - (double)b;
     o.b = sb + 16u * (uint32_t)b;
     const double2 g = lds128<MASS_BYTES + MR_G * NM * 16>(o.b);
-    const double eP = fexp<false>(fma(o.u, g.y, SHIFTED ? g.x + d : g.x), sb, rep);
-    o.EP = (m < K_SC[S_TOP]) ? eP : 0.0;          // -inf beyond the grid (:145); m <= 3 cannot happen once m >= 5
+    o.EP = fexp<false>(fma(o.u, g.y, SHIFTED ? g.x + d : g.x), sb, rep);   // m <= 3 cannot happen once m >= 5
     o.gy = g.y;
     o.m = m;
 }
@@ -198,7 +198,7 @@ __device__ __forceinline__ void eval_sample_fixed(USC_PARAM const double L, doub
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
     }
-    const double d = valid ? lin - A.m : 0.0;     // e^d is folded into the two exponentials of the mass function at m1
+    const double d = valid ? lin - A.m : ZERO_WEIGHT_SHIFT;   // e^d is folded into the two exponentials at m1
     A.nvalid += valid ? 1 : 0;
     const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb, rep);
     const double sr = frcp(1.0 + r);
@@ -206,7 +206,7 @@ __device__ __forceinline__ void eval_sample_fixed(USC_PARAM const double L, doub
     mass_eval<SLOT, true>(USC_ARG m1, lm1, d, sb, rep, M1);
     mass_eval<SLOT, false>(USC_ARG m2, lm2, 0.0, sb, rep, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
-    const double base = valid ? sr : 0.0;
+    const double base = sr;
     const double p = (sum1 * sum2) * base;
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
@@ -235,14 +235,20 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     j = min(max(j, 0), SRCH_N - 1);
     const uint32_t b0 = lds16<SRCH_BYTES>(sb + 2u * (uint32_t)j);
     const double knot = lds64<COS_BYTES + CR_DL * NZ * 16 + 16>(sb + 16u * b0);   // dl[b0 + 1]
-    const uint32_t b = min(b0 + (x >= knot ? 1u : 0u), (uint32_t)(NZ - 2));
+    // bin NZ-1 is the record BEYOND the table (x >= the last knot): the last knot's values with zero slopes and zero
+    // 1/width, i.e. t = 0, idl = 0 - jnp.interp clamps to fp[-1] and no gradient flows to x or xp - with no select
+    // here.  (The w0-wa kernel's knot-value tangent tables have no such slot: it clamps to the last bin and selects.)
+    const uint32_t b = min(b0 + (x >= knot ? 1u : 0u), (uint32_t)(WA ? NZ - 2 : NZ - 1));
     const uint32_t ab = sb + 16u * b;   // the bin's pair records
     const uint32_t at = sb + 8u * b;    // the bin's tangent-table knots (w0-wa mode)
     const double2 rdl = lds128<COS_BYTES + CR_DL * NZ * 16>(ab);
-    const bool beyond = x > K_SC[S_DL_LAST];          // jnp.interp clamps to fp[-1]; no gradient flows to x or xp
     double t = (x - rdl.x) * rdl.y;
-    const double idl = beyond ? 0.0 : rdl.y;
-    t = beyond ? 1.0 : t;
+    double idl = rdl.y;
+    if constexpr (WA) {
+        const bool beyond = x > K_SC[S_DL_LAST];
+        idl = beyond ? 0.0 : rdl.y;
+        t = beyond ? 1.0 : t;
+    }
     // ---- position inside the z bin: 1+z = (1+z_b)(1 + t eps)
     const double2 rz = lds128<COS_BYTES + CR_Z * NZ * 16>(ab);
     const double zeps = K_SC[S_ZEPS];
@@ -263,23 +269,28 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     // Zero weight (:149; log(dVc/dz = 0) = -inf).  Every intermediate of such a sample stays finite without any
     // substitution: samples that can never be valid (m2_det < mbh_min, i.e. m2 < 5 at every redshift) are replaced by
     // sentinels at upload, so here m1 >= m2 >= 5/101 and all exponents below are bounded; the weight is zeroed once.
-    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN) && (dvc > 0.0);
+    // (dVc/dz = 0, i.e. log(dVc/dz) = -inf in the reference, needs no test in linear space: the weight is a product
+    // with dvc)
+    const bool valid = (m1 >= MBH_MIN) && (m2 >= MBH_MIN);
     const double iddl = frcp(ddl);
     // ---- everything that is linear in precomputed logs: beta log(m1+m2) + log m1 + (lam-2) log1p(z) - log pdraw
     const double pair = lm1 + l1q;                  // log(m1+m2); the -beta log(60) is in the constant
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM2], L, -lpd);
     mid();
-    if (valid && lin - A.m > RESCALE_GAP) {         // also the first finite sample (m = -inf)
+    // e^{lin - shift} is not computed on its own: d is added to both exponents of the mass function at m1 (7 instead of
+    // 8 exponentials per sample; |d| <= RESCALE_GAP keeps the one-constant argument reduction at ~3e-14 relative)
+    // A sample without weight gets d = -5e4: both exponentials at m1 then return exp's saturation value (~1e-304
+    // relative to any real weight: below every rounding of the sums) - one select instead of zeroing the weight as well.
+    double d = valid ? lin - A.m : ZERO_WEIGHT_SHIFT;
+    if (d > RESCALE_GAP) {                          // also the first finite sample (shift = -inf: d = +inf)
         const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb, rep);
         A.a[0] *= s;
         A.a[1] *= s * s;
 #pragma unroll
         for (int k = 2; k < NACC; ++k) A.a[k] *= s;
         A.m = lin;
+        d = 0.0;
     }
-    // e^{lin - shift} is not computed on its own: d is added to both exponents of the mass function at m1 (7 instead of
-    // 8 exponentials per sample; |d| <= RESCALE_GAP keeps the one-constant argument reduction at ~3e-14 relative)
-    const double d = valid ? lin - A.m : 0.0;
     A.nvalid += valid ? 1 : 0;
     // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
     const double kappa = K_SC[S_KAPPA];
@@ -292,7 +303,7 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     mass_eval<SLOT, false>(USC_ARG m2, lm2, 0.0, sb, rep, M2);
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;   // sum1 carries e^{lin - shift}
     // ---- the weight and its partial products
-    const double base = valid ? sr * iddl : 0.0;    // everything but the masses and dVc/dz
+    const double base = sr * iddl;                  // everything but the masses and dVc/dz
     const double p0 = (sum1 * sum2) * base;         // weight / (dVc/dz)
     const double p = p0 * dvc;                      // e^{w - m}   (:381 / :388)
     const double bv = base * dvc;

@@ -138,17 +138,17 @@ constexpr int COS_EX0 = 80;         // offset of the neighbour-exchange area in 
 constexpr int PRO_SMEM_DOUBLES = COS_EX0 + COS_VALS * PRO_THREADS;
 static_assert(PRO_SMEM_DOUBLES >= 9 * NM + 64, "the PISN rows use 9 NM + 64 doubles of the same array");
 
-// One bin of the packed cosmology tables: lo / hi = the 13 numbers of its left / right knot, own = those of knot b
-// itself (differs from lo only for the padding record NZ-1).  Formats: bump_layout.cuh.
+// One bin of the packed cosmology tables: lo / hi = the 13 numbers of its left / right knot (both the last knot for the
+// beyond-the-table record NZ-1: all slopes zero), own = those of knot b itself.  Formats: bump_layout.cuh.
 __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo, const double* hi, const double* own,
                                                    double* __restrict__ blob, const EvalConsts ec, int& j0, int& j1) {
     j0 = j1 = 0;   // this bin's range of the d_L bucket table (empty in fixed-cosmology mode and for the padding bin)
     double2* cos = reinterpret_cast<double2*>(blob + OFF_COS);
     const int b0 = min(b, NZ - 2);
-    cos[CR_DL * NZ + b] = make_double2(lo[1], 1.0 / (hi[1] - lo[1]));
+    cos[CR_DL * NZ + b] = make_double2(lo[1], b <= NZ - 2 ? 1.0 / (hi[1] - lo[1]) : 0.0);
     cos[CR_DVC * NZ + b] = make_double2(lo[3], hi[3] - lo[3]);
     cos[CR_DDL * NZ + b] = make_double2(lo[2], hi[2] - lo[2]);
-    cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + lo[0]), b0 * ZSTEP);
+    cos[CR_Z * NZ + b] = make_double2(1.0 / (1.0 + lo[0]), b <= NZ - 2 ? b0 * ZSTEP : LOG_ZMAX1);
     if (ec.fixed) return;
     // tangent tables: value order [dl, ddl, dvc][Om, w, wa] -> blob order CosTan; knot values in w0-wa mode, per-bin
     // pairs {t_b, t_{b+1} - t_b} otherwise, nothing in fixed-cosmology mode
@@ -289,7 +289,10 @@ __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts 
     for (int r = 0; r < COS_VALS; ++r) ex[r * PRO_THREADS + threadIdx.x] = me[r];
     cluster.sync();
     double lo[COS_VALS], hi[COS_VALS];
-    const bool last_knot = (k == NZ - 1);   // record NZ-1 is padding: a copy of bin NZ-2 = [left neighbour, this knot]
+    // record NZ-1 is the bin BEYOND the table: the last knot's values with zero slopes, which is what jnp.interp returns
+    // for x > xp[-1] (fp[-1], no gradient through x) - the streaming kernel then needs no special case for such samples
+    // (w0-wa mode keeps knot-value tangent tables, which have no slot for it: that kernel clamps and selects instead)
+    const bool last_knot = (k == NZ - 1);
     if (!last_knot) {
         const double* src = (threadIdx.x + 1 < PRO_THREADS) ? ex + threadIdx.x + 1
                                                             : cluster.map_shared_rank(ex, chunk + 1);
@@ -297,7 +300,7 @@ __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts 
         for (int r = 0; r < COS_VALS; ++r) lo[r] = me[r], hi[r] = src[r * PRO_THREADS];
     } else {
 #pragma unroll
-        for (int r = 0; r < COS_VALS; ++r) lo[r] = ex[r * PRO_THREADS + threadIdx.x - 1], hi[r] = me[r];
+        for (int r = 0; r < COS_VALS; ++r) lo[r] = me[r], hi[r] = me[r];
     }
     int j0, j1;
     pack_cosmology_bin(k, lo, hi, me, blob, ec, j0, j1);
@@ -451,9 +454,15 @@ __device__ void pack_mass_records(const double* __restrict__ gtab /* shared copy
     double2* mass = reinterpret_cast<double2*>(blob + OFF_MASS);
     for (int item = t; item < NMREC * NM; item += nt) {
         const int r = item / NM, i = item - r * NM;
-        const int b0 = min(i, NM - 2);
-        const double g0 = gtab[r * NM + b0];
-        mass[item] = make_double2(g0, gtab[r * NM + b0 + 1] - g0);
+        if (i <= NM - 2) {
+            const double g0 = gtab[r * NM + i];
+            mass[item] = make_double2(g0, gtab[r * NM + i + 1] - g0);
+        } else {
+            // record NM-1 is the bin BEYOND the grid (m >= mbhmax + 7 sigma): log dN = -inf there (:145).  A value of
+            // -5e4 makes the kernel's exp return its saturation value (~1e-304 relative to the power-law term: below
+            // every rounding), with zero slope and zero tangents - no compare-and-select per sample in the kernel.
+            mass[item] = make_double2(r == MR_G ? MASS_BEYOND_LOG : 0.0, 0.0);
+        }
     }
 }
 
