@@ -526,6 +526,10 @@ def main():
                                     f"({pk.get('fp64_tflops', 'n/a')} TFLOP/s)" if "dfma_per_s" in pk else
                                     "fallback: DFMA rate measured on this pool's B200s in round 1 (bump_peak failed)",
                      "algorithmic_inst_per_sample": ALGO_FP64_INST_PER_SAMPLE,
+                     # the same against the FP64 issue rate AT THE SM CLOCK SAMPLED UNDER THIS LOAD: the peak above is
+                     # a short burst at the maximum clock, while an O5-size pass runs into the board's power cap
+                     "frac_at_sampled_clock": (inst / (fp64_rate * clocks["sm_mhz"] / clocks["sm_max_mhz"])
+                                               if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None),
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                              "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "peak_source": peak_src},
                      "note": "the path is transcendental-bound (8 exp + 4 reciprocals per sample, no contraction): the "
