@@ -282,7 +282,8 @@ def nuts_record(workload, warmup, samples, chains, device, cpu_s_per_eval=None):
     from bumpcosmology_b200 import intensity_models as im, nuts
     from bumpcosmology_b200.catalogs import make_catalog
     cat = make_catalog(workload)
-    models = [im.pop_cosmo_model(*cat.as_args(), device=device) for _ in range(chains)]
+    first = im.pop_cosmo_model(*cat.as_args(), device=device)
+    models = [first] + [first.clone() for _ in range(chains - 1)]   # one resident catalog, one context per chain
     t0 = time.perf_counter()
     r = nuts.run_mcmc(models, warmup, samples, chains, seed=1652819403, native=True)
     wall = time.perf_counter() - t0

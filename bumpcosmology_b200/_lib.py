@@ -28,6 +28,7 @@ SIGNATURES = {
     "bump_device_count": (C.c_int, []),
     "bump_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]),
     "bump_ctx_destroy": (None, [C.c_void_p]),
+    "bump_ctx_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bump_upload_events": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp]),
     "bump_upload_injections": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_double]),
     "bump_set_fixed_dvdzdt": (C.c_int, [C.c_void_p, _dp, C.c_int64]),

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -198,6 +199,17 @@ __global__ void math_probe_kernel(const int which, const double* __restrict__ x,
 struct DataSet {
     int64_t nrows = 0, ncols = 0, stride = 0;   // events: [nobs, nsamp]; injections: [1, nsel]
     double* base = nullptr;                     // nrows * stride / GROUP blocks of NCOL * GROUP doubles
+    // The resident columns are read-only after upload and may be shared by several contexts (bump_ctx_clone: one
+    // upload, one copy in HBM, one context per chain): freed by whoever drops the last reference.
+    std::shared_ptr<void> owner;
+    void reset() { *this = DataSet(); }
+    int alloc(size_t bytes) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return 1;
+        base = static_cast<double*>(p);
+        owner = std::shared_ptr<void>(p, [](void* q) { cudaFree(q); });
+        return 0;
+    }
 };
 
 }  // namespace
@@ -265,15 +277,15 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     if (c->fixed && !c->fixed_tab_set)
         return fail(BUMP_E_INVALID, "fixed-cosmology mode: call bump_set_fixed_dvdzdt before uploading data");
     if (int r = set_device(c)) return r;
-    cudaFree(ds.base);
-    ds = DataSet();
+    ds.reset();
     ds.nrows = nrows;
     ds.ncols = ncols;
     ds.stride = (ncols + GROUP - 1) / GROUP * GROUP;   // whole 64-sample groups: the kernel's loads are unpredicated
     c->plan_dirty = true;
     const int64_t n = nrows * ncols, npad = nrows * ds.stride;
     if (npad == 0) return BUMP_OK;
-    CK(cudaMalloc(&ds.base, sizeof(double) * NCOL * (npad + 2 * GROUP)));   // slack: the kernel prefetches two blocks ahead
+    if (ds.alloc(sizeof(double) * NCOL * (npad + 2 * GROUP)))   // slack: the kernel looks two blocks ahead
+        return fail(BUMP_E_CUDA, "cudaMalloc of the resident columns failed (out of device memory?)");
     double* raw = nullptr;
     CK(cudaMalloc(&raw, sizeof(double) * 4 * n));
     const double* src[4] = {m1d, q, dl, pd};
@@ -307,8 +319,7 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
     cudaFree(tmp), cudaFree(keys), cudaFree(keys_out), cudaFree(idx), cudaFree(perm);
     CK(cudaFree(raw));
     if (bad) {
-        cudaFree(ds.base);
-        ds = DataSet();
+        ds.reset();
         return fail(BUMP_E_INVALID, "input arrays must be finite and strictly positive (m1_det, q, d_L, pdraw)");
     }
     return BUMP_OK;
@@ -641,8 +652,8 @@ void bump_ctx_destroy(bump_ctx* c) {
     cudaFree(c->d_arena);
     cudaFree(c->d_plan_arena);
     cudaFree(c->d_peers);
-    cudaFree(c->evt.base);
-    cudaFree(c->sel.base);
+    c->evt.reset();
+    c->sel.reset();
     cudaFree(c->d_gather);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -663,6 +674,28 @@ int bump_upload_injections(bump_ctx* c, int64_t nsel, const double* m1s_det_sel,
     if (!(ndraw > 0.0)) return fail(BUMP_E_INVALID, "ndraw must be positive");
     c->ndraw = ndraw;
     return upload_set(c, c->sel, nsel > 0 ? 1 : 0, nsel, m1s_det_sel, qs_sel, dls_sel, pdraw_sel);
+}
+
+int bump_ctx_clone(bump_ctx* src, bump_ctx** out) {
+    if (!src || !out) return fail(BUMP_E_INVALID, "null argument");
+    *out = nullptr;
+    if (src->d_peers || src->comm) return fail(BUMP_E_INVALID, "clone a context before attaching a communicator");
+    bump_ctx* c = nullptr;
+    if (int r = bump_ctx_create(&c, src->device, src->flags)) return r;
+    if (src->fixed_tab_set) {
+        if (cudaMemcpy(c->d_fixed_tab, src->d_fixed_tab, sizeof(double) * NZ, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+            bump_ctx_destroy(c);
+            return fail(BUMP_E_CUDA, "copy of the fixed-cosmology table failed");
+        }
+        c->fixed_tab_set = true;
+    }
+    cudaStreamSynchronize(src->stream);   // uploads of the source are complete
+    c->evt = src->evt;                    // shares the resident columns (reference-counted)
+    c->sel = src->sel;
+    c->ndraw = src->ndraw;
+    c->plan_dirty = true;
+    *out = c;
+    return BUMP_OK;
 }
 
 int bump_set_fixed_dvdzdt(bump_ctx* c, const double* dvdzdt, int64_t n) {

@@ -41,6 +41,16 @@ class PopCosmoModel:
             self.like = self._local = Hyperlikelihood(*data, device=device)
         self.n_evals = 0
 
+    def clone(self):
+        """The same model on the same resident catalog with its own evaluation state: one per NUTS chain (the
+        reference's 4 chains share one data set, run_cosmo_fit.py:46-49).  Single-rank models only."""
+        if self.like is not self._local:
+            raise TypeError("clone() is for single-rank models (a sharded model's ranks step in lock step)")
+        new = object.__new__(PopCosmoModel)
+        new.like = new._local = self.like.clone()
+        new.n_evals = 0
+        return new
+
     # ---- site handling
     @staticmethod
     def _site_vector(sites):

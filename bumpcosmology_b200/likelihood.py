@@ -116,6 +116,20 @@ class Hyperlikelihood:
         self._out_p, self._theta_p = _lib.as_dp(self._out), _lib.as_dp(self._theta)
         self.plan()   # builds the execution plan now: every later call (also inside a stream capture) allocates nothing
 
+    def clone(self):
+        """A second evaluator on the SAME resident catalog (bump_ctx_clone): no upload, no second copy in HBM; theta,
+        tables, records and results are the clone's own, so the two evaluate concurrently (one per NUTS chain)."""
+        new = object.__new__(Hyperlikelihood)
+        for k in ("lib", "wa", "ntheta", "device", "fixed", "nobs", "nsamp", "nsel", "Ndraw"):
+            setattr(new, k, getattr(self, k))
+        new._ctx = C.c_void_p()
+        _lib.check(self.lib.bump_ctx_clone(self._ctx, C.byref(new._ctx)))
+        new._out = np.empty(int(self.lib.bump_out_len(new._ctx)), dtype=np.float64)
+        new._theta = np.zeros(_lib.NTHETA_MAX, dtype=np.float64)
+        new._out_p, new._theta_p = _lib.as_dp(new._out), _lib.as_dp(new._theta)
+        new.plan()
+        return new
+
     # -- lifetime
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:

@@ -60,7 +60,8 @@ def fit(pe, sel, num_warmup=NMCMC, num_samples=NMCMC, num_chains=NCHAIN, seed=RA
     (REFERENCE_DETERMINISTICS) plus the two factors."""
     from . import intensity_models as im, nuts
     args = inputs.model_arguments(pe, sel, cosmo)
-    models = [im.pop_cosmo_model(*args, device=device) for _ in range(num_chains)]   # one context per chain
+    first = im.pop_cosmo_model(*args, device=device)            # one upload, one copy of the catalog in HBM ...
+    models = [first] + [first.clone() for _ in range(num_chains - 1)]   # ... and one context per chain on it
     try:
         t0 = time.perf_counter()
         r = nuts.run_mcmc(models, num_warmup, num_samples, num_chains, seed=seed, native=native)

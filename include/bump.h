@@ -68,6 +68,12 @@ int bump_device_count(void);
 int bump_ctx_create(bump_ctx** ctx, int device, uint32_t flags);
 void bump_ctx_destroy(bump_ctx* ctx);
 
+/* A second context on the SAME resident catalog: the columns uploaded to `src` are shared (read-only, reference
+ * counted - one copy in HBM, freed with the last context), everything theta-dependent is the clone's own, so `src` and
+ * its clones evaluate different theta concurrently (one per NUTS chain: run_cosmo_fit.py:46 runs 4 chains on one data
+ * set).  Uploading to a clone detaches it from the shared columns.  Clone before attaching a communicator. */
+int bump_ctx_clone(bump_ctx* src, bump_ctx** clone);
+
 /* Upload this rank's events: four row-major [nobs, nsamp] float64 HOST arrays exactly as run_cosmo_fit.py:32-43
  * builds them (m1s_det, qs, dls, pdraw).  theta-independent logs are precomputed on the device here
  * (the reference recomputes log(pdraw) every trace, intensity_models.py:365).  nobs may be 0. */

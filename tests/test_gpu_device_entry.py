@@ -171,3 +171,32 @@ def test_peer_memory_exchange_path_with_a_single_rank(small):
     assert np.array_equal(like.raw(_thetas()[0]), plain.raw(_thetas()[0]), equal_nan=True)
     like.close()
     plain.close()
+
+
+def test_clones_share_the_resident_catalog_and_evaluate_independently(small):
+    """bump_ctx_clone: four chains on one upload.  Every clone returns what the original returns alone (bitwise), also
+    when all of them evaluate different theta from concurrent host threads, and the catalog survives the original."""
+    import threading
+    from bumpcosmology_b200.likelihood import Hyperlikelihood
+    first = Hyperlikelihood(*small.as_args())
+    likes = [first] + [first.clone() for _ in range(3)]
+    thetas = _thetas()
+    alone = [first.raw(th).copy() for th in thetas]
+    errors = []
+
+    def work(i):
+        for _ in range(100):
+            if not np.array_equal(likes[i].raw(thetas[i]), alone[i], equal_nan=True):
+                errors.append(i)
+                return
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    first.close()                                            # the clones keep the shared columns alive
+    assert np.array_equal(likes[2].raw(thetas[0]), alone[0], equal_nan=True)
+    for like in likes[1:]:
+        like.close()
