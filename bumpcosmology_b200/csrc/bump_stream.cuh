@@ -100,15 +100,116 @@ struct IC {   // integral constant (table ids as template arguments of generic l
 
 struct ThreadAcc {
     double m;           // shift
-    double a[NACC];     // S, S2, features
+    double a[NACC];     // S, S2, features (BUMP_TMEM_ACC: live only between a chunk's load and store inside a sample)
     int nvalid;
+    uint32_t taddr;     // BUMP_TMEM_ACC: this warp's accumulator columns in tensor memory
 };
+
+#ifdef BUMP_TMEM_ACC
+// ---- The 19 fp64 sums of a lane in TENSOR MEMORY instead of registers (no tensor-core math involved).  They cost 38
+// registers for the whole kernel and cap the CTA at 12 warps; at 128 registers 16 warps fit, and the kernel - bound
+// by the latencies of the FP64 pipe and of shared memory, no longer by issue slots - runs as fast as its warps hide
+// them (10 -> 12 warps per SM was +16 %).  Each warp owns 40 columns x its 32 lanes of the SM's tensor memory, as two
+// chunks of 10 doubles that a sample loads right before it updates them and stores right after:
+//   chunk R (columns 0..19) : S, S2, F_CZ, F_OM, F_W, F_WA, F_BETA, F_L, F_SIG, F_SIGL
+//   chunk M (columns 20..39): F_SQ, F_C, F_T, F_GEO, F_PA .. F_PSIGMA, (spare)
+constexpr int TMEM_COLS_PER_WARP = 40;
+constexpr int TMEM_ALLOC_COLS = 256;       // power of two >= (STREAM_WARPS / 4) * TMEM_COLS_PER_WARP
+static_assert((STREAM_WARPS + 3) / 4 * TMEM_COLS_PER_WARP <= TMEM_ALLOC_COLS, "tensor-memory columns");
+__device__ constexpr int ACC_CHUNK_R[10] = {0, 1, 2 + F_CZ, 2 + F_OM, 2 + F_W, 2 + F_WA, 2 + F_BETA, 2 + F_L, 2 + F_SIG, 2 + F_SIGL};
+__device__ constexpr int ACC_CHUNK_M[10] = {2 + F_SQ, 2 + F_C, 2 + F_T, 2 + F_GEO, 2 + F_PA, 2 + F_PB, 2 + F_PMPISN,
+                                            2 + F_PMBHMAX, 2 + F_PSIGMA, -1};
+
+__device__ __forceinline__ void tmem_ld20(const uint32_t taddr, uint32_t (&r)[20]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
+                 : "r"(taddr + 16));
+}
+__device__ __forceinline__ void tmem_st20(const uint32_t taddr, const uint32_t (&r)[20]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr + 16), "r"(r[16]), "r"(r[17]),
+                 "r"(r[18]), "r"(r[19]));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Warp-collective.  MASS = the chunk of the mass-function sums, else the chunk with S, S2 and the rest.
+template <bool MASS>
+__device__ __forceinline__ void acc_load(ThreadAcc& A) {
+    uint32_t r[20];
+    tmem_wait_st();   // the store of the previous sample to these columns
+    tmem_ld20(A.taddr + (MASS ? 20 : 0), r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int k = MASS ? ACC_CHUNK_M[i] : ACC_CHUNK_R[i];
+        if (k >= 0) A.a[k] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+    }
+}
+template <bool MASS>
+__device__ __forceinline__ void acc_store(const ThreadAcc& A) {
+    uint32_t r[20];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int k = MASS ? ACC_CHUNK_M[i] : ACC_CHUNK_R[i];
+        r[2 * i] = k >= 0 ? (uint32_t)__double2loint(A.a[k]) : 0u;
+        r[2 * i + 1] = k >= 0 ? (uint32_t)__double2hiint(A.a[k]) : 0u;
+    }
+    tmem_st20(A.taddr + (MASS ? 20 : 0), r);
+}
+#define ACC_LOAD_MASS(A) acc_load<true>(A)
+#define ACC_STORE_MASS(A) acc_store<true>(A)
+#define ACC_LOAD_REST(A) acc_load<false>(A)
+#define ACC_STORE_REST(A) acc_store<false>(A)
+#else
+#define ACC_LOAD_MASS(A)
+#define ACC_STORE_MASS(A)
+#define ACC_LOAD_REST(A)
+#define ACC_STORE_REST(A)
+#endif
 
 __device__ __forceinline__ void acc_init(ThreadAcc& A) {
     A.m = -INFINITY;
     A.nvalid = 0;
 #pragma unroll
     for (int k = 0; k < NACC; ++k) A.a[k] = 0.0;
+#ifdef BUMP_TMEM_ACC
+    acc_store<true>(A);
+    acc_store<false>(A);
+#endif
+}
+
+// Raise the shift of the accumulators to `lin` (rare: the first finite-weight sample of a record, or one that exceeds
+// the shift by e^RESCALE_GAP).  With the sums in tensor memory this is a warp-collective read-modify-write: lanes that
+// do not need it scale by 1.
+template <class Exp>
+__device__ __forceinline__ void acc_rescale(ThreadAcc& A, const bool need, const double lin, Exp&& exp_wide) {
+#ifdef BUMP_TMEM_ACC
+    if (!__any_sync(0xffffffffu, need)) return;
+    const double s = !need ? 1.0 : ((A.m == -INFINITY) ? 0.0 : exp_wide(A.m - lin));
+    acc_load<true>(A);
+    acc_load<false>(A);
+#else
+    if (!need) return;
+    const double s = (A.m == -INFINITY) ? 0.0 : exp_wide(A.m - lin);
+#endif
+    A.a[0] *= s;
+    A.a[1] *= s * s;
+#pragma unroll
+    for (int k = 2; k < NACC; ++k) A.a[k] *= s;
+    if (need) A.m = lin;
+#ifdef BUMP_TMEM_ACC
+    acc_store<true>(A);
+    acc_store<false>(A);
+#endif
 }
 
 // One mass-function evaluation in linear space: e^{A0(m)} = EP + EQ with EP = e^{PISN(m)} (:110-111,144-145),
@@ -190,14 +291,7 @@ __device__ __forceinline__ void eval_sample_fixed(USC_PARAM const double L, doub
     const double pair = lm1 + l1q;
     const double lin = fma(K_SC[S_BETA], pair, lm1) + fma(K_SC[S_LAM], L, -lpd);   // :332 (no (1+z)^-2 Jacobian here)
     mid();
-    if (valid && lin - A.m > RESCALE_GAP) {
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb, rep);
-        A.a[0] *= s;
-        A.a[1] *= s * s;
-#pragma unroll
-        for (int k = 2; k < NACC; ++k) A.a[k] *= s;
-        A.m = lin;
-    }
+    acc_rescale(A, valid && lin - A.m > RESCALE_GAP, lin, [&](const double x) { return fexp<true>(x, sb, rep); });
     const double d = valid ? lin - A.m : ZERO_WEIGHT_SHIFT;   // e^d is folded into the two exponentials at m1
     A.nvalid += valid ? 1 : 0;
     const double r = fexp<false>(K_SC[S_KAPPA] * (L - K_SC[S_LOPZP]), sb, rep);
@@ -208,15 +302,19 @@ __device__ __forceinline__ void eval_sample_fixed(USC_PARAM const double L, doub
     const double sum1 = M1.EP + M1.EQ, sum2 = M2.EP + M2.EQ;
     const double base = sr;
     const double p = (sum1 * sum2) * base;
-    A.a[0] += p;
-    A.a[1] = fma(p, p, A.a[1]);
+    ACC_LOAD_MASS(A);
     mass_features<SLOT>(USC_ARG M1, sum2 * base, A.a);
     mass_features<SLOT>(USC_ARG M2, sum1 * base, A.a);
+    ACC_STORE_MASS(A);
+    ACC_LOAD_REST(A);
+    A.a[0] += p;
+    A.a[1] = fma(p, p, A.a[1]);
     const double psig = p * (r * sr);
     A.a[2 + F_BETA] = fma(p, pair, A.a[2 + F_BETA]);
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
     A.a[2 + F_SIG] += psig;
     A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
+    ACC_STORE_REST(A);
 }
 
 // `mid()` runs once every input of the sample has been consumed (used by the caller to issue the next loads there:
@@ -282,14 +380,10 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     // A sample without weight gets d = -5e4: both exponentials at m1 then return exp's saturation value (~1e-304
     // relative to any real weight: below every rounding of the sums) - one select instead of zeroing the weight as well.
     double d = valid ? lin - A.m : ZERO_WEIGHT_SHIFT;
-    if (d > RESCALE_GAP) {                          // also the first finite sample (shift = -inf: d = +inf)
-        const double s = (A.m == -INFINITY) ? 0.0 : fexp<true>(A.m - lin, sb, rep);
-        A.a[0] *= s;
-        A.a[1] *= s * s;
-#pragma unroll
-        for (int k = 2; k < NACC; ++k) A.a[k] *= s;
-        A.m = lin;
-        d = 0.0;
+    {
+        const bool need = d > RESCALE_GAP;          // also the first finite sample (shift = -inf: d = +inf)
+        acc_rescale(A, need, lin, [&](const double x) { return fexp<true>(x, sb, rep); });
+        if (need) d = 0.0;
     }
     A.nvalid += valid ? 1 : 0;
     // ---- merger-rate density (:173): (1+z)^lam / (1 + r),  r = ((1+z)/(1+zp))^kappa
@@ -307,9 +401,12 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     const double p0 = (sum1 * sum2) * base;         // weight / (dVc/dz)
     const double p = p0 * dvc;                      // e^{w - m}   (:381 / :388)
     const double bv = base * dvc;
+    ACC_LOAD_MASS(A);
+    const double md = mass_features<SLOT>(USC_ARG M1, sum2 * bv, A.a) + mass_features<SLOT>(USC_ARG M2, sum1 * bv, A.a);
+    ACC_STORE_MASS(A);
+    ACC_LOAD_REST(A);
     A.a[0] += p;
     A.a[1] = fma(p, p, A.a[1]);
-    const double md = mass_features<SLOT>(USC_ARG M1, sum2 * bv, A.a) + mass_features<SLOT>(USC_ARG M2, sum1 * bv, A.a);
     // ---- d w / d t at fixed tables (times p), then the cosmological tangents
     const double lt = zeps * u1;                    // d log1p(z) / dt
     const double psig = p * sig;
@@ -339,11 +436,16 @@ __device__ __forceinline__ void eval_sample(USC_PARAM const double x, const doub
     A.a[2 + F_L] = fma(p, L, A.a[2 + F_L]);
     A.a[2 + F_SIG] += psig;
     A.a[2 + F_SIGL] = fma(psig, L, A.a[2 + F_SIGL]);
+    ACC_STORE_REST(A);
 }
 
 // Warp-wide merge of the per-lane accumulators (fixed shuffle tree: deterministic) -> one record.
 __device__ __forceinline__ void warp_flush(ThreadAcc& A, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
+#ifdef BUMP_TMEM_ACC
+    acc_load<true>(A);
+    acc_load<false>(A);
+#endif
     double mx = A.m;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -387,6 +489,17 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     constexpr int BLOB_BYTES = blob_doubles(WA, FIXED) * 8;   // the mode's share of the blob (bump_layout.cuh)
     double* s_blob = reinterpret_cast<double*>(smem_raw);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);   // inside the (unused) scalar block
+#ifdef BUMP_TMEM_ACC
+    // tensor memory for the accumulators: one warp allocates, everybody reads the base address after the barrier
+    // inside stage_tables (the address lands in the unused scalar block, behind the mbarrier)
+    uint32_t* tmem_base = reinterpret_cast<uint32_t*>(smem_raw + 16);
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base)),
+                     "n"(TMEM_ALLOC_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+#endif
 
 #ifdef BUMP_SCALARS_FROM_BLOB
     // Build option BUMP_SCALARS_FROM_BLOB: no constant bank at all (no copy node in the evaluation graph, no constant-bank
@@ -419,6 +532,16 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     uint32_t sb = smem_u32(smem_raw);
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));
 
+#ifdef BUMP_TMEM_ACC
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // a warp reaches only its own quarter of the 128 tensor-memory lanes (warp id mod 4); the warps of one quarter get
+    // disjoint column ranges
+    const uint32_t tmem_addr = *tmem_base + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) +
+                               (uint32_t)((threadIdx.x >> 7) * TMEM_COLS_PER_WARP);
+#endif
+    // everything one warp does after the staging (it may return early; the kernel frame below owns the final barrier
+    // of the tensor-memory variant)
+    auto warp_work = [&]() {
     const int lane = threadIdx.x & 31;
     const uint32_t rep = (uint32_t)(lane & (EXPT_REPL - 1)) << 3;   // this lane's copy of the exp-table entries
     uint64_t l2_stream_policy;
@@ -448,6 +571,9 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     int e = e_first;
     int k = (e < wk.nobs) ? g0 - e * g_evt : g0 - n_evt_groups;
     ThreadAcc A;
+#ifdef BUMP_TMEM_ACC
+    A.taddr = tmem_addr;
+#endif
     acc_init(A);
     // The loads are software-pipelined at half-group granularity - y(g) is issued before x(g) is evaluated, x(g+1)
     // from inside the evaluation of y(g) - so every load has one sample evaluation (~800 cycles) to land, at no
@@ -546,6 +672,17 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         atomicMax(tl + 2 * TL_STREAM_WARPS + 1, t);
         if (warp < TL_WARP_SLOTS) tl[2 * TL_N + warp] = t;   // bump_debug_warp_times
     }
+    };   // warp_work
+    warp_work();
+#ifdef BUMP_TMEM_ACC
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base), "n"(TMEM_ALLOC_COLS));
+    }
+#endif
 }
 
 #undef K_SC
