@@ -68,12 +68,13 @@ def shard_catalog(data, rank, world):
 
 
 def unpack_header(out, ntheta):
-    return dict(loglike=float(out[_lib.OUT_LOGLIKE]), log_mu_sel=float(out[_lib.OUT_LOG_MU_SEL]),
-                log_mu2=float(out[_lib.OUT_LOG_MU2]), neff_sel=float(out[_lib.OUT_NEFF_SEL]),
-                dloglike=np.array(out[_lib.OUT_DLOGLIKE:_lib.OUT_DLOGLIKE + ntheta]),
-                dlog_mu_sel=np.array(out[_lib.OUT_DLOG_MU:_lib.OUT_DLOG_MU + ntheta]),
-                nobs=int(out[_lib.OUT_NOBS]), nsel=int(out[_lib.OUT_NSEL]),
-                nvalid_evt=int(out[_lib.OUT_NVALID_EVT]), nvalid_sel=int(out[_lib.OUT_NVALID_SEL]))
+    h = out[:_lib.OUT_HEADER].tolist()   # one conversion to Python floats (this runs once per evaluation)
+    return dict(loglike=h[_lib.OUT_LOGLIKE], log_mu_sel=h[_lib.OUT_LOG_MU_SEL], log_mu2=h[_lib.OUT_LOG_MU2],
+                neff_sel=h[_lib.OUT_NEFF_SEL],
+                dloglike=out[_lib.OUT_DLOGLIKE:_lib.OUT_DLOGLIKE + ntheta].copy(),
+                dlog_mu_sel=out[_lib.OUT_DLOG_MU:_lib.OUT_DLOG_MU + ntheta].copy(),
+                nobs=int(h[_lib.OUT_NOBS]), nsel=int(h[_lib.OUT_NSEL]),
+                nvalid_evt=int(h[_lib.OUT_NVALID_EVT]), nvalid_sel=int(h[_lib.OUT_NVALID_SEL]))
 
 
 class Hyperlikelihood:
@@ -151,10 +152,15 @@ class Hyperlikelihood:
 
     # -- evaluation through HOST buffers (the reference-facing call: h2d of theta, d2h of the result inside)
     def __call__(self, theta):
-        th = self._set_theta(theta)
-        _lib.check(self.lib.bump_eval(self._ctx, _lib.as_dp(th), _lib.as_dp(self._out)))
-        hdr = unpack_header(self._out, self.ntheta)
-        return Evaluation(neff=self._out[_lib.OUT_HEADER:].copy(), **hdr)
+        if np.shape(theta) != (self.ntheta,):
+            self._set_theta(theta)           # raises with the list of parameter names (or accepts a column vector)
+        else:
+            self._theta[:self.ntheta] = theta
+        code = self.lib.bump_eval(self._ctx, self._theta_p, self._out_p)
+        if code:
+            _lib.check(code)
+        out = self._out
+        return Evaluation(neff=out[_lib.OUT_HEADER:].copy(), **unpack_header(out, self.ntheta))
 
     def raw(self, theta):
         """Same evaluation, no wrapping: returns the library's output vector (a view that the next call overwrites):
