@@ -53,22 +53,37 @@ void grad_from_features(const double* phi, const double n, const double* sc, dou
     if (sc[S_FIXED] != 0.0) g[T_H] = g[T_OM] = g[T_W] = g[T_WA] = 0.0;   // pop_model: the cosmology is not a parameter
 }
 
-// partials: [nranks][PARTIAL_LEN] in rank order -> out[OUT_HEADER]
-__host__ __device__ inline void finalize_merge(const double* partials, const int nranks, double* out) {
+// partials: [nranks][PARTIAL_LEN] in rank order -> out[OUT_HEADER], in two independent halves (the last block of the
+// epilogue runs them in two warps at once; the host-side merge calls them one after the other): the events' factor ...
+__host__ __device__ inline void finalize_events(const double* partials, const int nranks, double* out) {
     const double* sc = partials + P_SCAL0;   // identical on every rank (same theta)
-    double llsum = 0.0, nobs = 0.0, nvalid_e = 0.0, nvalid_s = 0.0, nsel = 0.0, ndead = 0.0;
+    double llsum = 0.0, nobs = 0.0, nvalid_e = 0.0, ndead = 0.0;
     double phi[NFEAT];
     for (int k = 0; k < NFEAT; ++k) phi[k] = 0.0;
-    double M = -INFINITY;
     for (int r = 0; r < nranks; ++r) {
         const double* p = partials + (size_t)r * PARTIAL_LEN;
         llsum += p[P_LLSUM];
         nobs += p[P_NOBS];
         nvalid_e += p[P_NVALID_EVT];
-        nvalid_s += p[P_NVALID_SEL];
-        nsel += p[P_NSEL];
         ndead += p[P_NDEAD_EVT];
         for (int k = 0; k < NFEAT; ++k) phi[k] += p[P_FSUM0 + k];
+    }
+    // 'loglike' factor (:382-383)
+    out[OUT_LOGLIKE] = (ndead > 0.0) ? -INFINITY : llsum + nobs * (sc[S_CONST] - sc[S_LOG_NSAMP]);
+    grad_from_features(phi, nobs, sc, out + OUT_DLOGLIKE);
+    out[OUT_NVALID_EVT] = nvalid_e;
+    out[OUT_NOBS] = nobs;
+}
+
+// ... and the injections' (:389-394)
+__host__ __device__ inline void finalize_selection(const double* partials, const int nranks, double* out) {
+    const double* sc = partials + P_SCAL0;
+    double nvalid_s = 0.0, nsel = 0.0;
+    double M = -INFINITY;
+    for (int r = 0; r < nranks; ++r) {
+        const double* p = partials + (size_t)r * PARTIAL_LEN;
+        nvalid_s += p[P_NVALID_SEL];
+        nsel += p[P_NSEL];
         M = fmax(M, p[P_SEL_M]);
     }
     double acc[NACC];
@@ -81,12 +96,7 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
         acc[1] += p[P_SEL_ACC0 + 1] * (s * s);
         for (int k = 2; k < NACC; ++k) acc[k] += p[P_SEL_ACC0 + k] * s;
     }
-    for (int k = 0; k < OUT_HEADER; ++k) out[k] = 0.0;
     const double cst = sc[S_CONST];
-    // events: 'loglike' factor (:382-383)
-    out[OUT_LOGLIKE] = (ndead > 0.0) ? -INFINITY : llsum + nobs * (cst - sc[S_LOG_NSAMP]);
-    grad_from_features(phi, nobs, sc, out + OUT_DLOGLIKE);
-    // injections (:389-394)
     const double lnd = sc[S_LOG_NDRAW];
     const double log_mu = M + log(acc[0]) + cst - lnd;
     const double log_mu2 = 2.0 * M + log(acc[1]) + 2.0 * cst - 2.0 * lnd;
@@ -98,13 +108,20 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
     const double iS = 1.0 / acc[0];
     for (int k = 0; k < NFEAT; ++k) phis[k] = acc[2 + k] * iS;
     grad_from_features(phis, 1.0, sc, out + OUT_DLOG_MU);
-    if (sc[S_BAD] != 0.0) {   // theta outside the support: the reference yields NaN (NUTS treats it as divergent)
+    out[OUT_NVALID_SEL] = nvalid_s;
+    out[OUT_NSEL] = nsel;
+}
+
+// theta outside the support: the reference yields NaN (NUTS treats it as divergent)
+__host__ __device__ inline bool finalize_is_bad(const double* partials) { return partials[P_SCAL0 + S_BAD] != 0.0; }
+
+__host__ __device__ inline void finalize_merge(const double* partials, const int nranks, double* out) {
+    for (int k = 0; k < OUT_HEADER; ++k) out[k] = 0.0;
+    finalize_events(partials, nranks, out);
+    finalize_selection(partials, nranks, out);
+    if (finalize_is_bad(partials)) {
         for (int k = 0; k < OUT_NVALID_EVT; ++k) out[k] = NAN;
     }
-    out[OUT_NVALID_EVT] = nvalid_e;
-    out[OUT_NVALID_SEL] = nvalid_s;
-    out[OUT_NOBS] = nobs;
-    out[OUT_NSEL] = nsel;
 }
 
 // ---- fused exchange over peer memory (NVLink): every rank owns a mailbox that all peers can write.
@@ -370,6 +387,14 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     }
     __threadfence();
     timeline_begin(tl, TL_EPI_LAST);
+    __shared__ double s_part[P2P_MAX_RANKS * PARTIAL_LEN];
+    __shared__ double s_out[OUT_HEADER];
+    __shared__ double s_sel[8 * EPI_SLOT];   // the injection blocks' (shift, sums)
+    // Everything this block reads from L2 is requested up front, so that the round trips overlap: the injection
+    // blocks' (shift, sums), the scalar block (both consumed further down) and the event blocks' slots.
+    static_assert(8 * EPI_SLOT <= EPI_THREADS, "one thread per staged value");
+    const double sel_v = (tid < nb_sel * EPI_SLOT) ? __ldcg(slots + (size_t)nb_evt * EPI_SLOT + tid) : 0.0;
+    const double scal_v = (tid >= P_SCAL0 && tid < P_SCAL0 + NSCAL) ? __ldcg(blob + OFF_SCAL + tid - P_SCAL0) : 0.0;
     {   // column k of the slots, summed by 8 threads (blocks p, p + 8, ...) and then over p in a fixed order
         const int k = tid & 31, p = tid >> 5;
         static_assert(NFEAT + 3 <= 32 && EPI_THREADS == 256, "8 x 32 threads cover the slot columns");
@@ -380,6 +405,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
         }
         __syncthreads();   // `red` was last used by the block sums above
         red[32 + p * 32 + k] = s;
+        if (tid < nb_sel * EPI_SLOT) s_sel[tid] = sel_v;
         __syncthreads();
         if (tid < NFEAT + 3) {
             double t = 0.0;
@@ -392,12 +418,6 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     // this rank's partial: to global memory (host-driven / NCCL exchanges read it there) and to shared memory, from
     // which one thread finalizes - its ~250 dependent operations then run on 30-cycle shared-memory loads instead of
     // L2 round trips (the serial tail was half of the epilogue's time at GWTC-3 size)
-    __shared__ double s_part[P2P_MAX_RANKS * PARTIAL_LEN];
-    __shared__ double s_out[OUT_HEADER];
-    __shared__ double s_sel[8 * EPI_SLOT];   // the injection blocks' (shift, sums): one load each, all in flight together
-    if (tid < nb_sel * EPI_SLOT) s_sel[tid] = __ldcg(slots + (size_t)nb_evt * EPI_SLOT + tid);
-    static_assert(8 * EPI_SLOT <= EPI_THREADS, "one thread per staged value");
-    __syncthreads();
     if (tid < P_SCAL0 + NSCAL) {
         double v = 0.0;
         if (tid < P_SCAL0) {
@@ -424,7 +444,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
             }
             else if (tid == P_NSEL) v = nsel;
         } else {
-            v = __ldcg(blob + OFF_SCAL + tid - P_SCAL0);
+            v = scal_v;
         }
         partial[tid] = v;
         s_part[tid] = v;
@@ -445,17 +465,24 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
                 for (int k = tid; k < nparts * PARTIAL_LEN; k += EPI_THREADS) s_part[k] = __ldcg(mail + k);
             }
         }
+        if (tid < OUT_HEADER) s_out[tid] = 0.0;
         __syncthreads();
-        if (tid == 0) {
-            if (status == STATUS_OK) {
-                finalize_merge(s_part, nparts, s_out);
-            } else {   // the exchange failed on every rank (see p2p_exchange): no result, and say so
-                for (int k = 0; k < OUT_HEADER; ++k) s_out[k] = (k < OUT_NVALID_EVT) ? NAN : 0.0;
-                s_out[OUT_STATUS] = status;
-            }
+        // the two factors are independent chains of ~120 dependent operations each: one thread of warp 0 takes the
+        // events', one of warp 1 the injections'
+        if (status == STATUS_OK) {
+            if (tid == 0) finalize_events(s_part, nparts, s_out);
+            if (tid == 32) finalize_selection(s_part, nparts, s_out);
         }
         __syncthreads();
-        if (tid < OUT_HEADER) out_header[tid] = s_out[tid];
+        if (tid < OUT_HEADER) {
+            double v = s_out[tid];
+            if (status != STATUS_OK) {   // the exchange failed on every rank (see p2p_exchange): no result, and say so
+                v = (tid < OUT_NVALID_EVT) ? NAN : (tid == OUT_STATUS ? status : 0.0);
+            } else if (finalize_is_bad(s_part) && tid < OUT_NVALID_EVT) {
+                v = NAN;
+            }
+            out_header[tid] = v;
+        }
     }
     timeline_end(tl, TL_EPI_LAST);
     timeline_end(tl, TL_EPILOGUE);

@@ -325,6 +325,16 @@ __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts 
     int bad = 0;
 #pragma unroll
     for (int r = 1; r < COS_VALS; ++r) bad |= !isfinite(me[r]);
+    // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is exact unless
+    // one of the two clamped end buckets spans more than two bins (first: every x below 2^-8 (1 + 1/256) Gpc must lie in
+    // bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the last two bins).  That takes roughly h > 7 or
+    // h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).  Checked by the two threads that own those knots.
+    if (!ec.fixed) {
+        const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
+        const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
+        if (k == 2) bad |= !(dl.v >= first_hi);
+        if (k == NZ - 3) bad |= !(dl.v <= last_lo);
+    }
     return bad;
 }
 
@@ -479,7 +489,7 @@ static_assert(PRO_BLOCKS % COS_CHUNKS == 0, "the grid is a whole number of clust
 
 __global__ void __cluster_dims__(COS_CHUNKS, 1, 1) __launch_bounds__(PRO_THREADS)
 prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
-                unsigned int* __restrict__ flags /* [0] ticket, [1] bad, [2] rows ticket */, const EvalConsts ec,
+                unsigned int* __restrict__ flags /* [0] ticket (low half) + bad count (high half), [2] rows ticket */, const EvalConsts ec,
                 unsigned long long* __restrict__ tl) {
     __shared__ double sm[PRO_SMEM_DOUBLES];
     __shared__ double th[NTHETA_MAX];
@@ -497,9 +507,14 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     timeline_end(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     // (the PISN table is checked by the row block that finishes last, below)
+    // The verdict travels in the upper half of the ticket word (every block adds 1 + 0x10000 if it saw something bad),
+    // so that the block that finishes last knows it from the value its own ticket returns: no second round trip.
+    __shared__ unsigned int s_bad;
+    if (threadIdx.x == 0) s_bad = 0u;
     if (is_cos) {
         if (threadIdx.x < NTHETA_MAX) bad |= !isfinite(th[threadIdx.x]);
-        if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
+        const int any_bad = __syncthreads_or(bad);
+        if (threadIdx.x == 0) s_bad = any_bad ? 1u : 0u;
     }
     // ---- the LAST ROW block (rows ticket): once all 256 PISN rows exist, the scalars (seven forward-mode chains of
     // ~1000 dependent FP64 instructions each: the longest serial piece of the prologue) and the packed mass records.
@@ -525,7 +540,10 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
                     bad_g |= !isfinite(g[r]);
                 }
             }
-            if (__syncthreads_or(bad_g) && threadIdx.x == 0) atomicOr(flags + 1, 1u);
+            {
+                const int any_bad = __syncthreads_or(bad_g);
+                if (threadIdx.x == 0 && any_bad) s_bad = 1u;
+            }
             if (threadIdx.x < 32) {
                 build_scalars(th, gtab, ec, blob + OFF_SCAL, threadIdx.x);
                 if (threadIdx.x == 0) flags[2] = 0u;   // re-arm the rows ticket
@@ -539,19 +557,13 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     // ---- the block that finishes last of all (global ticket): the validity flag, and re-arming
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(flags, 1u) == gridDim.x - 1) {
-        __threadfence();
-        // The streaming kernel takes a single step from srch[j]: a bucket is narrower than any bin, so that is
-        // exact unless one of the two clamped end buckets spans more than two bins (first: every x below
-        // 2^-8 (1 + 1/256) Gpc must lie in bin 0 or 1; last: every x above 2^13 (1 - 1/256) Gpc in one of the
-        // last two bins).  That takes roughly h > 7 or h < 0.11 (prior: 0.35 .. 1.4): flag it (-> NaN outputs).
-        const double first_hi = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + 1) << (20 - SRCH_MBITS), 0);
-        const double last_lo = __hiloint2double(((SRCH_EXP_LO << SRCH_MBITS) + SRCH_N - 1) << (20 - SRCH_MBITS), 0);
-        unsigned int f = atomicOr(flags + 1, 0u);
-        if (!ec.fixed && (!(__ldcg(aux + AUX_DL + 2) >= first_hi) || !(__ldcg(aux + AUX_DL + NZ - 3) <= last_lo))) f = 1u;
-        blob[OFF_SCAL + S_BAD] = (f != 0u) ? 1.0 : 0.0;
-        flags[0] = 0u;   // re-arm the ticket and the bad flag for the next evaluation
-        flags[1] = 0u;
+    if (threadIdx.x == 0) {
+        const unsigned int mine = 1u + (s_bad ? 0x10000u : 0u);
+        const unsigned int old = atomicAdd(flags, mine);
+        if ((old & 0xffffu) == gridDim.x - 1) {
+            blob[OFF_SCAL + S_BAD] = ((old + mine) >> 16) != 0u ? 1.0 : 0.0;
+            flags[0] = 0u;   // re-arm the ticket for the next evaluation
+        }
     }
     timeline_end(tl, TL_PROLOGUE);
 }
