@@ -261,6 +261,7 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     __shared__ double s_max;
     __shared__ bool is_last;
     const int tid = threadIdx.x;
+    pdl_wait<PDL_EPILOGUE>();   // scheduled while the stream kernel drains: its records (and the prologue's scalars) are complete after this
     timeline_begin(tl, TL_EPILOGUE);
     const int nobs = wk.nobs;
     const int epb = EPI_THREADS / lpe;   // events per block

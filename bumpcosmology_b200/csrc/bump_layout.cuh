@@ -196,6 +196,43 @@ enum TimelineSlot { TL_PROLOGUE = 0, TL_STREAM, TL_EPILOGUE, TL_FINALIZE,
                     TL_N };
 constexpr int TL_WARP_SLOTS = 4096;   // per-warp end times of the streaming kernel behind the phase slots
 #ifdef __CUDACC__
+// Programmatic dependent launch (see launch_dependent in bump_lib.cu).  `launch_dependents`: the next kernel on the
+// stream may be scheduled once every block of this grid has said so (or exited).  `wait`: returns when the kernel in
+// front of this one has completed and its memory is visible; a no-op for a kernel launched in plain stream order.
+// Measured on B200 (profiles/r02_ab_experiments.md, GWTC-3 shape, same box):
+//   stream kernel -> epilogue, dependents released when the stream kernel's blocks exit (default): -0.7 us
+//   ... released when the first warp of every block is done (BUMP_PDL_EPI_TRIGGER=1):              -0.6 us
+//   ... released at kernel start (=2): +3.6 us - the waiting epilogue blocks pile up on the few SMs that have
+//       room beside a stream-kernel block instead of spreading over all of them
+//   prologue -> stream kernel as well (BUMP_PDL_STREAM): nothing on top (the stream kernel needs a whole SM's shared
+//       memory, so it cannot start beside a prologue block), and with dependents released at the prologue's start
+//       concurrent contexts returned WRONG results (the stream kernel's constant-bank reads are only ordered
+//       against the prologue's writes by a launch that follows the prologue's completion).  Off, and not to be used.
+#ifdef BUMP_PDL_STREAM
+constexpr bool PDL_STREAM = true;      // prologue -> stream kernel (measurement option, see above)
+#else
+constexpr bool PDL_STREAM = false;
+#endif
+#ifdef BUMP_NO_PDL
+constexpr bool PDL_EPILOGUE = false;
+#else
+constexpr bool PDL_EPILOGUE = true;    // stream kernel -> epilogue
+#endif
+#ifndef BUMP_PDL_EPI_TRIGGER
+#define BUMP_PDL_EPI_TRIGGER 0   // 0: when the stream kernel's blocks exit, 1: when their first warp is done, 2: at their start
+#endif
+#ifndef BUMP_PDL_STREAM_TRIGGER
+#define BUMP_PDL_STREAM_TRIGGER 0   // 0: when the prologue's blocks exit, 2: at their start
+#endif
+template <bool ON>
+__device__ __forceinline__ void pdl_launch_dependents() {
+    if (ON) asm volatile("griddepcontrol.launch_dependents;");
+}
+template <bool ON>
+__device__ __forceinline__ void pdl_wait() {
+    if (ON) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

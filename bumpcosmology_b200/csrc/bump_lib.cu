@@ -1,9 +1,10 @@
 // libbump_b200.so — C ABI (include/bump.h) over the sm_100a kernels.  CUDA runtime only; no torch, no CPU fallback.
 //
-// One evaluation = 3 kernel launches (+ one 512-byte device-to-device copy) replayed from a CUDA graph:
+// One evaluation = 3 kernel launches replayed from a CUDA graph, the second and third as programmatic dependents of
+// their predecessors (their blocks are scheduled while the predecessor drains and wait in griddepcontrol.wait):
 //   prologue_kernel  (bump_tables.cuh)   theta -> PISN and cosmology tables + tangents (F1-F2 of SURVEY.md 2.2), then
-//                                        in its last block the packed per-bin records, d_L bucket table, scalars (F3)
-//   (copy node)                          the scalars -> this context's constant-bank slot
+//                                        in its last block the packed per-bin records, d_L bucket table, scalars (F3;
+//                                        the scalars also go straight into this context's constant-bank slot)
 //   stream_kernel    (bump_stream.cuh)   one pass over the SoA columns -> per-warp records (F4-F7 + reverse pass)
 //   epilogue_kernel  (bump_epilogue.cuh) per-event logsumexp / Neff, rank partial, and (single rank, or peer-memory
 //                                        exchange) the result
@@ -217,6 +218,7 @@ struct DataSet {
 struct bump_ctx {
     int device = 0;
     int slot = 0;                     // constant-bank slot of the streaming kernel's scalars (0 .. NSLOT-1)
+    double* d_cbank = nullptr;        // global address of that slot (the prologue writes it), null: copy node instead
     uint32_t flags = 0;
     bool use_wa = false;
     bool fixed = false;               // fixed-cosmology mode (pop_model)
@@ -412,25 +414,49 @@ StreamKernel stream_kernel_at(const bool fixed, const bool wa, const int slot) {
 static_assert(NSLOT == 4, "stream_kernel_at enumerates the slots");
 StreamKernel stream_kernel_for(const bump_ctx* c) { return stream_kernel_at(c->fixed, c->use_wa, c->slot); }
 
-// The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches and one 512-byte copy.
+// A launch that may begin before the kernel in front of it on the stream has finished (programmatic dependent launch):
+// its blocks are scheduled as soon as every block of the predecessor has executed griddepcontrol.launch_dependents and
+// an SM has room, and they must execute griddepcontrol.wait before touching anything the predecessor writes (the wait
+// returns when the predecessor has completed and its writes are visible).  Inside a captured graph the edge becomes a
+// programmatic dependency.  What it buys is the launch latency between two kernels (~1 us each, of a ~45 us
+// evaluation at GWTC-3 size).  BUMP_NO_PDL: plain stream order.
+template <class... KArgs, class... Args>
+cudaError_t launch_dependent(const bool programmatic, void (*kernel)(KArgs...), const dim3 grid, const dim3 block,
+                             const size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = programmatic ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr,
                    unsigned long long* tl = nullptr) {
-    prologue_kernel<<<PRO_BLOCKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_ticket + 4, consts_of(c), tl);
-#ifndef BUMP_SCALARS_FROM_BLOB
+    prologue_kernel<<<PRO_BLOCKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_cbank, c->d_ticket + 4,
+                                                       consts_of(c), tl);
+#if !defined(BUMP_SCALARS_FROM_BLOB) && defined(BUMP_CBANK_COPY_NODE)
     CK(cudaMemcpyToSymbolAsync(K_SC4, c->d_blob + OFF_SCAL, sizeof(double) * NSCAL,
                                sizeof(double) * NSCAL * c->slot, cudaMemcpyDeviceToDevice, s));
 #endif
     if (k0) cudaEventRecord(k0, s);
     if (c->work.n_groups > 0)
-        stream_kernel_for(c)<<<c->grid, STREAM_THREADS, stream_smem_bytes(c->use_wa, c->fixed), s>>>(
-            columns_of(c), c->work, c->d_rec_off, c->d_blob, c->d_part, tl);
+        CK(launch_dependent(PDL_STREAM, stream_kernel_for(c), dim3(c->grid), dim3(STREAM_THREADS),
+                            stream_smem_bytes(c->use_wa, c->fixed), s, columns_of(c), c->work, c->d_rec_off, c->d_blob,
+                            c->d_part, tl));
     if (k1) cudaEventRecord(k1, s);
     const int epb = EPI_THREADS / c->lpe;
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
-    epilogue_kernel<<<nb_evt + c->nb_sel, EPI_THREADS, 0, s>>>(c->d_part, c->d_rec_off, c->work, (double)c->sel.ncols,
-                                                               c->lpe, c->nb_sel, c->d_blob, neff_dev, c->d_slots, c->d_ticket + 1, partial_dev,
-                                                       fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl);
+    CK(launch_dependent(PDL_EPILOGUE, epilogue_kernel, dim3(nb_evt + c->nb_sel), dim3(EPI_THREADS), 0, s, c->d_part, c->d_rec_off,
+                        c->work, (double)c->sel.ncols, c->lpe, c->nb_sel, c->d_blob, neff_dev, c->d_slots,
+                        c->d_ticket + 1, partial_dev, fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl));
     CK(cudaGetLastError());
     return BUMP_OK;
 }
@@ -620,6 +646,13 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         ++g_slot_users[device * NSLOT + best];
         c->slot_counted = true;
     }
+#if !defined(BUMP_SCALARS_FROM_BLOB) && !defined(BUMP_CBANK_COPY_NODE)
+    {
+        void* p = nullptr;
+        CK(cudaGetSymbolAddress(&p, K_SC4));
+        c->d_cbank = static_cast<double*>(p) + (size_t)NSCAL * c->slot;
+    }
+#endif
     CK(cudaFuncSetAttribute(stream_kernel_for(c), cudaFuncAttributeMaxDynamicSharedMemorySize,
                             stream_smem_bytes(c->use_wa, c->fixed)));
     {

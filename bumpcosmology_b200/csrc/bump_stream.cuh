@@ -484,6 +484,7 @@ template <bool WA, bool FIXED, int SLOT>
 __global__ void BUMP_STREAM_BOUNDS
 stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off,
               const double* __restrict__ g_blob, double* __restrict__ part, unsigned long long* __restrict__ tl) {
+    pdl_launch_dependents<PDL_EPILOGUE && BUMP_PDL_EPI_TRIGGER == 2>();   // (measurement option: at kernel start)
     timeline_begin(tl, TL_STREAM);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int BLOB_BYTES = blob_doubles(WA, FIXED) * 8;   // the mode's share of the blob (bump_layout.cuh)
@@ -501,14 +502,17 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
     asm volatile("tcgen05.fence::before_thread_sync;");
 #endif
 
+    // This grid may have been scheduled while the prologue was still running: nothing theta-dependent (the blob, the
+    // constant-bank slot) is touched before this returns.
+    pdl_wait<PDL_STREAM>();
 #ifdef BUMP_SCALARS_FROM_BLOB
-    // Build option BUMP_SCALARS_FROM_BLOB: no constant bank at all (no copy node in the evaluation graph, no constant-bank
-    // slots shared between contexts).  Lane l fetches scal[l] and scal[32 + l] from the blob in global memory (the loads
+    // Build option BUMP_SCALARS_FROM_BLOB: no constant bank at all (no constant-bank slots shared between contexts).
+    // Lane l fetches scal[l] and scal[32 + l] from the blob in global memory (the loads
     // fly while the tables are staged), and every scalar the loop needs is broadcast from its lane: a shuffle from a
     // fixed lane is a value the compiler knows to be warp-uniform.  ptxas promotes only three such values to uniform
     // registers, though (it hoists a dozen constant-bank loads into them): measured on B200 the streaming kernel is 4 %
-    // slower this way (0.0190 against 0.0183 ns per sample), and the copy node costs only ~2 us inside a graph, so the
-    // constant bank stays the default.
+    // slower this way (0.0190 against 0.0183 ns per sample), and the constant bank costs nothing per evaluation (the
+    // prologue writes the slot itself), so it stays the default.
     const double sc_lo = __ldcg(g_blob + OFF_SCAL + (threadIdx.x & 31));
     const double sc_hi = __ldcg(g_blob + OFF_SCAL + 32 + (threadIdx.x & 31));
 #endif
@@ -672,6 +676,8 @@ stream_kernel(const Columns cols, const Work wk, const int* __restrict__ rec_off
         atomicMax(tl + 2 * TL_STREAM_WARPS + 1, t);
         if (warp < TL_WARP_SLOTS) tl[2 * TL_N + warp] = t;   // bump_debug_warp_times
     }
+    // the epilogue's blocks may be scheduled once the first warp of every block is done (they then wait for the rest)
+    pdl_launch_dependents<PDL_EPILOGUE && BUMP_PDL_EPI_TRIGGER == 1>();
     };   // warp_work
     warp_work();
 #ifdef BUMP_TMEM_ACC

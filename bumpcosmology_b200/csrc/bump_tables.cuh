@@ -183,9 +183,23 @@ __device__ __forceinline__ void pack_cosmology_bin(const int b, const double* lo
     }
 }
 
+// Where the prologue puts a scalar: into the blob's scalar block (read by the epilogue and by the debugging entry
+// points) and, unless the build takes the stream kernel's scalars from the blob, straight into the context's slot of
+// the constant bank through the slot's global address.  A kernel may not write constant memory that IT reads; the
+// prologue never reads K_SC4, and the stream kernel that does is a later launch.  (Round 1 copied the 512 bytes with
+// a device-to-device copy node between the two kernels: ~1.1 us of every evaluation.)
+struct ScalarSink {
+    double* blob_scal;
+    double* cbank;   // may be null
+    __device__ __forceinline__ void set(const int i, const double v) const {
+        blob_scal[i] = v;
+        if (cbank) cbank[i] = v;
+    }
+};
+
 // Returns non-zero if one of this thread's table values is not finite (theta outside the prior support).
 __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts ec, double* __restrict__ aux,
-                                double* __restrict__ blob, double* sm, const int chunk) {
+                                double* __restrict__ blob, const ScalarSink scal, double* sm, const int chunk) {
     const int use_wa = ec.use_wa;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -277,8 +291,8 @@ __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts 
                            dvc.d[0], dvc.d[1], dvc.d[2]};
 #pragma unroll
     for (int r = 0; r < COS_VALS; ++r) aux[r * NZ + k] = me[r];   // raw knots (bump_debug_tables)
-    if (k == 0) blob[OFF_SCAL + S_DL_FIRST] = dl.v;
-    if (k == NZ - 1) blob[OFF_SCAL + S_DL_LAST] = dl.v;
+    if (k == 0) scal.set(S_DL_FIRST, dl.v);
+    if (k == NZ - 1) scal.set(S_DL_LAST, dl.v);
     static_assert(AUX_ZG == 0 && AUX_DL == NZ && AUX_DDL == 2 * NZ && AUX_DVC == 3 * NZ && AUX_TAN == 4 * NZ,
                   "aux order of the 13 cosmology value sets");
     // ---- packed per-bin records, straight from the registers: bin b = [knot b, knot b+1] needs the right neighbour's
@@ -346,7 +360,8 @@ __device__ int cosmology_tables(const double* __restrict__ th, const EvalConsts 
 // before lane 3 v joins them with two shuffles (this is the longest serial piece of the whole prologue: ~1000 dependent
 // FP64 instructions per chain unsplit).  Lane 21 derives the rate normalisation (-self(zref = 0), :168,173), lane 22
 // the theta-only numbers.  gtab = [6][NM] copy of aux[AUX_G ...] in shared memory.
-__device__ void build_scalars(const double* th, const double* gtab, const EvalConsts ec, double* scal, const int lane) {
+__device__ void build_scalars(const double* th, const double* gtab, const EvalConsts ec, const ScalarSink scal,
+                              const int lane) {
     typedef Dual<1> D;
     const int v = lane / 3, sub = lane - 3 * v;
     D piece(0.0);        // this lane's piece of chain v
@@ -399,35 +414,35 @@ __device__ void build_scalars(const double* th, const double* gtab, const EvalCo
         const double r0 = exp(-kappa * lopzp);
         lnV = log1p(r0);
         const double sig0 = r0 / (1.0 + r0);
-        scal[S_KAPPA] = kappa;
-        scal[S_ZP] = zp;
-        scal[S_LOPZP] = lopzp;
-        scal[S_RATE_LOG_NORM] = lnV;
-        scal[S_LNV_KAPPA] = -sig0 * lopzp;
-        scal[S_LNV_ZP] = -sig0 * kappa / (1.0 + zp);
+        scal.set(S_KAPPA, kappa);
+        scal.set(S_ZP, zp);
+        scal.set(S_LOPZP, lopzp);
+        scal.set(S_RATE_LOG_NORM, lnV);
+        scal.set(S_LNV_KAPPA, -sig0 * lopzp);
+        scal.set(S_LNV_ZP, -sig0 * kappa / (1.0 + zp));
     } else if (lane == 22) {
         const double M = th[T_MBHMAX], top = M + 7.0 * th[T_SIGMA];
-        scal[S_H] = th[T_H];
-        scal[S_INV_H] = 1.0 / th[T_H];
-        scal[S_C] = th[T_C];
-        scal[S_M] = M;
-        scal[S_LOG_M] = log(M);
-        scal[S_INV_DM] = 1.0 / (M * TURNON_WIDTH);
-        scal[S_TOP] = top;
+        scal.set(S_H, th[T_H]);
+        scal.set(S_INV_H, 1.0 / th[T_H]);
+        scal.set(S_C, th[T_C]);
+        scal.set(S_M, M);
+        scal.set(S_LOG_M, log(M));
+        scal.set(S_INV_DM, 1.0 / (M * TURNON_WIDTH));
+        scal.set(S_TOP, top);
         const double inv_dmbh = (NM - 1) / (top - MIN_BH_MASS);
-        scal[S_INV_DMBH] = inv_dmbh;
-        scal[S_INV_TOPM3] = 1.0 / (top - MIN_BH_MASS);
-        scal[S_BETA] = th[T_BETA];
-        scal[S_LAM] = th[T_LAM];
-        scal[S_FPL] = th[T_FPL];
-        scal[S_LOG_NSAMP] = ec.log_nsamp;
-        scal[S_LOG_NDRAW] = ec.log_ndraw;
-        scal[S_USE_WA] = (double)ec.use_wa;
-        scal[S_FIXED] = (double)ec.fixed;
-        scal[S_ZEPS] = expm1(ZSTEP);
-        scal[S_POS0] = -MIN_BH_MASS * inv_dmbh;
-        scal[S_LAM2] = th[T_LAM] - 2.0;
-        scal[S_RATE0] = th[T_LAM] - 3.0 - th[T_BETA];
+        scal.set(S_INV_DMBH, inv_dmbh);
+        scal.set(S_INV_TOPM3, 1.0 / (top - MIN_BH_MASS));
+        scal.set(S_BETA, th[T_BETA]);
+        scal.set(S_LAM, th[T_LAM]);
+        scal.set(S_FPL, th[T_FPL]);
+        scal.set(S_LOG_NSAMP, ec.log_nsamp);
+        scal.set(S_LOG_NDRAW, ec.log_ndraw);
+        scal.set(S_USE_WA, (double)ec.use_wa);
+        scal.set(S_FIXED, (double)ec.fixed);
+        scal.set(S_ZEPS, expm1(ZSTEP));
+        scal.set(S_POS0, -MIN_BH_MASS * inv_dmbh);
+        scal.set(S_LAM2, th[T_LAM] - 2.0);
+        scal.set(S_RATE0, th[T_LAM] - 3.0 - th[T_BETA]);
     }
     __syncwarp();
     // join: lane 3 v (sub 0) takes PISN(mref) from lane 3 v + 1 and the power-law piece from lane 3 v + 2
@@ -444,16 +459,16 @@ __device__ void build_scalars(const double* th, const double* gtab, const EvalCo
         const int map5[5] = {0, 1, 3, 4, 5};
 #pragma unroll
         for (int q = 0; q < 5; ++q)
-            if (map5[q] == v) scal[S_LPN_D0 + q] = lpn.d[0];
+            if (map5[q] == v) scal.set(S_LPN_D0 + q, lpn.d[0]);
     }
-    scal[S_LN_D0 + v] = ln.d[0];
+    scal.set(S_LN_D0 + v, ln.d[0]);
     if (v != 0) return;
-    scal[S_LPN] = lpn.v;
-    scal[S_LOG_NORM] = ln.v;
-    scal[S_EXP_LPN] = exp(lpn.v);
-    scal[S_C2] = 2.0 * exp(lpn.v);
-    scal[S_LOG_C2] = LN2 + lpn.v;
-    scal[S_CONST] = 2.0 * ln.v + lnV - th[T_BETA] * LOG_MREF_PAIR;
+    scal.set(S_LPN, lpn.v);
+    scal.set(S_LOG_NORM, ln.v);
+    scal.set(S_EXP_LPN, exp(lpn.v));
+    scal.set(S_C2, 2.0 * exp(lpn.v));
+    scal.set(S_LOG_C2, LN2 + lpn.v);
+    scal.set(S_CONST, 2.0 * ln.v + lnV - th[T_BETA] * LOG_MREF_PAIR);
 }
 
 // ---------------------------------------------------------------- packed mass records (last block of the prologue)
@@ -489,8 +504,11 @@ static_assert(PRO_BLOCKS % COS_CHUNKS == 0, "the grid is a whole number of clust
 
 __global__ void __cluster_dims__(COS_CHUNKS, 1, 1) __launch_bounds__(PRO_THREADS)
 prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, double* __restrict__ blob,
-                unsigned int* __restrict__ flags /* [0] ticket (low half) + bad count (high half), [2] rows ticket */, const EvalConsts ec,
-                unsigned long long* __restrict__ tl) {
+                double* __restrict__ cbank /* global address of the context's constant-bank slot, or null */,
+                unsigned int* __restrict__ flags /* [0] ticket (low half) + bad count (high half), [2] rows ticket */,
+                const EvalConsts ec, unsigned long long* __restrict__ tl) {
+    pdl_launch_dependents<PDL_STREAM && BUMP_PDL_STREAM_TRIGGER == 2>();   // (measurement option: at kernel start)
+    const ScalarSink scal = {blob + OFF_SCAL, cbank};
     __shared__ double sm[PRO_SMEM_DOUBLES];
     __shared__ double th[NTHETA_MAX];
     __shared__ bool is_last;
@@ -503,7 +521,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
     timeline_begin(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     int bad = 0;
     if (!is_cos) pisn_row(th, row, aux, sm);
-    else bad = cosmology_tables(th, ec, aux, blob, sm, blockIdx.x);
+    else bad = cosmology_tables(th, ec, aux, blob, scal, sm, blockIdx.x);
     timeline_end(tl, is_cos ? TL_PRO_COSMO : TL_PRO_ROWS);
     // non-finite tables (theta outside the prior support) or theta: flag it, finalize returns NaN.
     // (the PISN table is checked by the row block that finishes last, below)
@@ -545,7 +563,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
                 if (threadIdx.x == 0 && any_bad) s_bad = 1u;
             }
             if (threadIdx.x < 32) {
-                build_scalars(th, gtab, ec, blob + OFF_SCAL, threadIdx.x);
+                build_scalars(th, gtab, ec, scal, threadIdx.x);
                 if (threadIdx.x == 0) flags[2] = 0u;   // re-arm the rows ticket
             } else {
                 pack_mass_records(gtab, blob, threadIdx.x - 32, PRO_THREADS - 32);
@@ -561,7 +579,7 @@ prologue_kernel(const double* __restrict__ theta, double* __restrict__ aux, doub
         const unsigned int mine = 1u + (s_bad ? 0x10000u : 0u);
         const unsigned int old = atomicAdd(flags, mine);
         if ((old & 0xffffu) == gridDim.x - 1) {
-            blob[OFF_SCAL + S_BAD] = ((old + mine) >> 16) != 0u ? 1.0 : 0.0;
+            scal.set(S_BAD, ((old + mine) >> 16) != 0u ? 1.0 : 0.0);
             flags[0] = 0u;   // re-arm the ticket for the next evaluation
         }
     }

@@ -102,8 +102,8 @@ int bump_eval(bump_ctx* ctx, const double* theta, double* out);
 
 /* Same, fully asynchronous on a caller stream with DEVICE pointers (what an XLA FFI handler calls):
  * no allocation, no host synchronisation.  stream is a cudaStream_t passed as void*.  The stream may be CAPTURING
- * (an XLA command buffer, torch.cuda.graph): the evaluation then becomes 3 kernel nodes and one 512-byte copy node of
- * the caller's graph.  Capture needs (a) the plan built beforehand (bump_plan_info or one evaluation after the uploads)
+ * (an XLA command buffer, torch.cuda.graph): the evaluation then becomes 3 kernel nodes of the caller's graph (the
+ * epilogue as a programmatic dependent of the stream kernel).  Capture needs (a) the plan built beforehand (bump_plan_info or one evaluation after the uploads)
  * and (b) a context that owns its constant-bank slot alone, i.e. at most 4 contexts alive on the device; the slot
  * stays reserved for the captured context until it is destroyed.  A context is not re-entrant: do not run two of its
  * evaluations (captured or not) concurrently.  out_dev[BUMP_OUT_STATUS] reports a failed multi-rank exchange. */

@@ -49,6 +49,34 @@ def test_eval_device_equals_host_call(small):
     like.close()
 
 
+def test_queued_evaluations_with_changing_theta(small):
+    """48 evaluations queued back to back on one stream with no host synchronisation in between, theta changing every
+    time: each kernel of evaluation k + 1 is on the GPU's queue while evaluation k still runs (and the dependent
+    kernels of one evaluation are scheduled early), so a scalar or table taken from the neighbouring evaluation
+    would give that evaluation's result.  Bitwise against the same theta evaluated alone."""
+    import torch
+    from bumpcosmology_b200 import _lib
+    from bumpcosmology_b200.likelihood import Hyperlikelihood
+    like = Hyperlikelihood(*small.as_args())
+    thetas = _thetas()
+    alone = [like.raw(th).copy() for th in thetas]
+    n = 48
+    stream = torch.cuda.Stream()
+    th_d = torch.zeros(n, _lib.NTHETA_MAX, dtype=torch.float64, device="cuda")
+    out_d = torch.zeros(n, _lib.OUT_HEADER + like.nobs, dtype=torch.float64, device="cuda")
+    order = [(5 * k + k // 4) % len(thetas) for k in range(n)]
+    for k, j in enumerate(order):
+        th_d[k, :14] = torch.from_numpy(thetas[j])
+    torch.cuda.synchronize()
+    for k in range(n):
+        like.eval_device(th_d[k].data_ptr(), out_d[k].data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    got = out_d.cpu().numpy()
+    for k, j in enumerate(order):
+        assert np.array_equal(got[k], alone[j], equal_nan=True), (k, j)
+    like.close()
+
+
 def test_eval_device_under_stream_capture(small):
     import torch
     from bumpcosmology_b200 import _lib

@@ -210,6 +210,24 @@ def test_repeat_evaluations_are_bitwise_identical(hl):
     like.close()
 
 
+def test_alternating_theta_never_sees_the_previous_evaluation(golden_dir, hl):
+    """The prologue writes the theta-dependent scalars straight into the constant bank, and the stream kernel and the
+    epilogue are programmatic dependents that may be scheduled before their predecessor has finished: a read that
+    came too early, or a constant served from a cache line of the previous evaluation, would show up as the result
+    of the OTHER theta (or a mix).  Back-to-back graph replays with theta changing every time, checked bitwise
+    against each theta's first result."""
+    g = _load(golden_dir, "small")
+    like = hl(*_data(g))
+    thetas = [np.array(t, dtype=float) for t in g["thetas"]]
+    first = [like.raw(t).copy() for t in thetas]
+    for k, t in enumerate(thetas):   # the first pass itself is right (against the reference's goldens)
+        assert _close(first[k][0], g["ref_loglike"][k]), k
+    for rep in range(300):
+        k = (rep * 7 + rep // 3) % len(thetas)
+        assert np.array_equal(like.raw(thetas[k]), first[k], equal_nan=True), (rep, k)
+    like.close()
+
+
 def test_host_model_mirror_matches_reference_sites_and_curves(golden_dir):
     """bumpcosmology_b200.intensity_models.pop_cosmo_model: same signature and site names as the reference;
     factors, deterministics, site gradients and the 128-point diagnostic curves against the goldens."""
