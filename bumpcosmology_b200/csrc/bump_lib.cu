@@ -98,21 +98,50 @@ constexpr int NCCL_FLOAT64 = 8;   // ncclDouble in nccl.h
                                          (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
     } while (0)
 
+// Host -> device copy that is complete, in the context's (non-blocking) stream order AND for the host, when it returns.
+// A plain cudaMemcpy from pageable memory returns once the data is staged - the DMA into device memory may still be
+// running - and it is ordered against the legacy default stream only, which a non-blocking stream does not wait for:
+// a kernel launched on c->stream right afterwards could read the tail of the buffer before it arrived (seen once the
+// reciprocal probe of bump_debug_math ran right behind its 2.4 MB input copy: NaN in the last few thousand entries).
+#define H2D_SYNC(c, dst, src, bytes)                                                              \
+    do {                                                                                          \
+        CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (c)->stream));          \
+        CK(cudaStreamSynchronize((c)->stream));                                                   \
+    } while (0)
+
 // ---- upload-time kernel: raw (m1_det, q, d_L, pdraw) -> the 7 padded SoA columns (theta-independent logs hoisted;
 // the reference recomputes log(pdraw) on every trace, intensity_models.py:365)
 
-// Locality key of a sample: (row | coarse d_L bucket | fine m1_det).  Sorting the samples of an event (the
-// likelihood is a sum over them, so their order is free) makes the 32 lanes of a warp land in the same or in
-// neighbouring bins of the d_L tables and of the mass table at m1: shared-memory reads become broadcasts /
-// conflict-free instead of random (DESIGN.md "sample order").
-__global__ void locality_keys_kernel(const double* __restrict__ m1d, const double* __restrict__ dl,
-                                     const int64_t ncols, const int64_t n, unsigned long long* __restrict__ keys,
-                                     unsigned int* __restrict__ idx) {
+// Locality key of a sample.  Sorting the samples of an event (the likelihood is a sum over them, so their order is
+// free) makes the 32 lanes of a warp land in the same or in neighbouring records of the d_L tables and of the mass
+// table - at m1 AND at m2 = q m1: a shared-memory read of 16-byte records is conflict-free when the 8 lanes of a
+// quarter-warp hit records that are equal or less than 8 apart (DESIGN.md "sample order").
+//   key = row | d_L bucket (1/16 octave) | m1_det bucket (4 % wide) | m2_det (fine, 1/128 in log), the direction of
+//   the last field alternating from one m1 bucket to the next so that the walk through the (m1, m2) plane is continuous.
+// The buckets are in detector-frame quantities (theta-independent); inside one d_L bucket (1 + z) is the same for every
+// sample to a few percent whatever the cosmology, so neighbours in (m1_det, m2_det) are neighbours in the source
+// frame too.  Round 1's key (d_L 1/32 octave | m1_det fine) left m2 unordered: 6.7 wavefronts per LDS.128 at m2
+// against a floor of 4 (ncu, O5 mock), 15 % of the kernel's shared-memory wavefronts (build option
+// BUMP_SORT_KEY_M1_ONLY keeps it for comparison).
+__global__ void locality_keys_kernel(const double* __restrict__ m1d, const double* __restrict__ q,
+                                     const double* __restrict__ dl, const int64_t ncols, const int64_t n,
+                                     unsigned long long* __restrict__ keys, unsigned int* __restrict__ idx) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long row = (unsigned long long)(i / ncols);
+        const unsigned long long row = (unsigned long long)(i / ncols);   // < 2^27 (checked by the caller)
+#ifdef BUMP_SORT_KEY_M1_ONLY
         const unsigned int kd = ((unsigned int)__double2hiint(dl[i]) >> 15) & 0xFFFFu;        // 1/32-octave buckets
         const unsigned int km = (unsigned int)min(max((__double2hiint(m1d[i]) - (1023 << 20)) >> 4, 0), 0xFFFFF);
         keys[i] = (row << 36) | ((unsigned long long)kd << 20) | km;
+#else
+        // (non-finite or non-positive inputs are rejected by prepare_columns_kernel right after; here they only
+        // have to produce SOME key)
+        const unsigned int kd = ((unsigned int)__double2hiint(dl[i]) >> 16) & 0x7FFFu;        // exponent + 4 mantissa bits
+        const double lm1 = log(m1d[i]), lm2 = lm1 + log(q[i]);
+        const int km = min(max((int)floor(lm1 * 25.0) + 512, 0), 1023);                       // 0.04 in log m1_det
+        int k2 = min(max((int)floor((lm2 + 8.0) * 128.0), 0), 4095);                          // 1/128 in log m2_det
+        if (km & 1) k2 = 4095 - k2;
+        keys[i] = (row << 37) | ((unsigned long long)kd << 22) | ((unsigned long long)km << 12) | (unsigned long long)k2;
+#endif
         idx[i] = (unsigned int)i;
     }
 }
@@ -304,7 +333,7 @@ int upload_set(bump_ctx* c, DataSet& ds, int64_t nrows, int64_t ncols, const dou
         CK(cudaMalloc(&keys_out, sizeof(unsigned long long) * n));
         CK(cudaMalloc(&idx, sizeof(unsigned int) * n));
         CK(cudaMalloc(&perm, sizeof(unsigned int) * n));
-        locality_keys_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + 2 * n, ncols, n, keys, idx);
+        locality_keys_kernel<<<blocks, 256, 0, c->stream>>>(raw, raw + n, raw + 2 * n, ncols, n, keys, idx);
         size_t tmp_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, idx, perm, n, 0, 64, c->stream));
         CK(cudaMalloc(&tmp, tmp_bytes));
@@ -376,7 +405,7 @@ int build_plan(bump_ctx* c) {
         c->d_part = reinterpret_cast<double*>(base + b_out + b_slots + b_rec);
     }
     CK(cudaMallocHost(&c->h_out, sizeof(double) * c->out_len));
-    CK(cudaMemcpy(c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size(), cudaMemcpyHostToDevice));
+    H2D_SYNC(c, c->d_rec_off, rec_off.data(), sizeof(int) * rec_off.size());
     c->plan_dirty = false;
     return BUMP_OK;
 }
@@ -610,6 +639,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
                      o_epoch = take(2 * sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * (2 * TL_N + TL_WARP_SLOTS));
         CK(cudaMalloc(&c->d_arena, off));
         CK(cudaMemset(c->d_arena, 0, off));
+        CK(cudaDeviceSynchronize());   // (a memset of device memory is asynchronous, and c->stream does not wait for the default stream)
         char* base = static_cast<char*>(c->d_arena);
         c->d_theta = reinterpret_cast<double*>(base + o_theta);
         c->d_aux = reinterpret_cast<double*>(base + o_aux);
@@ -624,7 +654,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         std::vector<double> expt(EXPT_DOUBLES);
         for (int j = 0; j < NEXPT; ++j)
             for (int r = 0; r < EXPT_REPL; ++r) expt[j * EXPT_REPL + r] = (double)exp2l((long double)j / NEXPT);
-        CK(cudaMemcpy(c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * EXPT_DOUBLES, cudaMemcpyHostToDevice));
+        H2D_SYNC(c, c->d_blob + OFF_EXPT, expt.data(), sizeof(double) * EXPT_DOUBLES);
     }
     // [0] unused, [1] epilogue ticket, [2] unused, [3] bad-input flag, [4] prologue ticket, [5] bad-theta flag
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
@@ -736,7 +766,7 @@ int bump_set_fixed_dvdzdt(bump_ctx* c, const double* dvdzdt, int64_t n) {
     if (!c->fixed) return fail(BUMP_E_INVALID, "context was not created with BUMP_FLAG_FIXED_COSMO");
     if (n != NZ) return fail(BUMP_E_INVALID, "the dVdzdt table must have 1024 entries (zinterp of intensity_models.py:324)");
     if (int r = set_device(c)) return r;
-    CK(cudaMemcpy(c->d_fixed_tab, dvdzdt, sizeof(double) * NZ, cudaMemcpyHostToDevice));
+    H2D_SYNC(c, c->d_fixed_tab, dvdzdt, sizeof(double) * NZ);
     c->fixed_tab_set = true;
     return BUMP_OK;
 }
@@ -878,7 +908,7 @@ int bump_p2p_attach(bump_ctx* c, const void* handles, int nranks, int rank) {
         p.box[r] = static_cast<Mailbox*>(ptr);
     }
     if (!c->d_peers) CK(cudaMalloc(&c->d_peers, sizeof(Peers)));
-    CK(cudaMemcpy(c->d_peers, &p, sizeof(p), cudaMemcpyHostToDevice));
+    H2D_SYNC(c, c->d_peers, &p, sizeof(p));
     c->h_peers = p;
     c->nranks = nranks;
     c->rank = rank;
@@ -911,7 +941,7 @@ int bump_p2p_set_timeout(bump_ctx* c, double seconds) {
     if (c->d_peers) {
         CK(cudaStreamSynchronize(c->stream));
         c->h_peers.timeout_ns = (unsigned long long)(seconds * 1e9);
-        CK(cudaMemcpy(c->d_peers, &c->h_peers, sizeof(Peers), cudaMemcpyHostToDevice));
+        H2D_SYNC(c, c->d_peers, &c->h_peers, sizeof(Peers));
     }
     return BUMP_OK;
 }
@@ -940,7 +970,7 @@ int bump_debug_math(bump_ctx* c, int which, const double* x, int64_t n, double* 
     double *dx = nullptr, *dy = nullptr;
     CK(cudaMalloc(&dx, sizeof(double) * n));
     CK(cudaMalloc(&dy, sizeof(double) * n));
-    CK(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    H2D_SYNC(c, dx, x, sizeof(double) * n);
     const int smem = (OFF_EXPT + EXPT_DOUBLES) * 8;
     CK(cudaFuncSetAttribute(math_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     math_probe_kernel<<<64, 256, smem, c->stream>>>(which, dx, n, c->d_blob, dy);
