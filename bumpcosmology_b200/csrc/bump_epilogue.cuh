@@ -125,23 +125,30 @@ __host__ __device__ inline void finalize_merge(const double* partials, const int
 }
 
 // ---- fused exchange over peer memory (NVLink): every rank owns a mailbox that all peers can write.
-// mail[parity][rank][PARTIAL_LEN] receives rank's partial of the evaluation with that parity, flag[parity][rank] its
-// epoch.  The last block of the epilogue pushes this rank's partial into every mailbox (its own included), publishes
-// the epoch, waits until its own mailbox holds the current epoch from every rank, and finalizes — no NCCL call, no
-// extra launch.  Two parities: a rank can run at most one evaluation ahead of the slowest peer (it needs that peer's
-// current partial to finish), so the buffer it overwrites is never still being read.
+// The last block of the epilogue pushes this rank's 1 KiB partial into every mailbox (its own included), waits until
+// its own mailbox holds the current evaluation's partial of every rank, and finalizes - no NCCL call, no extra launch.
+//
+// The transport is a low-latency line protocol (the idea of NCCL's LL): every double travels as ONE 16-byte line
+// {low word, epoch, high word, epoch}, written with a single 16-byte store.  Each 8-byte half carries its own copy of
+// the 32-bit epoch, so the receiver needs nothing but 8-byte store atomicity: it polls the line until both epochs are
+// the current one, and then holds the data.  No fence between data and flag, no flag round trip, no second read of the
+// mailbox: one NVLink one-way latency from "partial ready" to "partial received" (the first version - data, system
+// fence, flag, poll, system fence, read - cost two NVLink round trips more: ~5 us of every multi-rank evaluation).
+// line[parity][rank][k]: two parities, because a rank can run at most one evaluation ahead of the slowest peer (it
+// needs that peer's current partial to finish), so the lines it overwrites have been consumed; a line of parity p is
+// next written two epochs later, and its stale epoch never equals the awaited one.
 //
 // Failure is COLLECTIVE and STICKY.  A rank that waits longer than `timeout_ns` for a peer gives up, does NOT advance
-// its epoch, marks its exchange state broken and overwrites its flag in every peer's mailbox (both parities) with
-// P2P_POISON; a peer that is waiting for it - or arrives later, however late - finds the poison instead of the epoch,
-// fails the same way and poisons everybody else in turn.  Every evaluation after that fails immediately until the
-// ranks detach and attach again.  The result header carries the status word (OUT_STATUS) next to NaN outputs, and
-// bump_eval returns BUMP_E_EXCHANGE: ranks can no longer disagree about whether an evaluation happened.
+// its epoch, marks its exchange state broken and sets flag[both parities][its rank] in every peer's mailbox to
+// P2P_POISON; a peer that is waiting for its lines - or arrives later, however late - finds the poison, fails the same
+// way and poisons everybody else in turn.  Every evaluation after that fails immediately until the ranks detach and
+// attach again.  The result header carries the status word (OUT_STATUS) next to NaN outputs, and bump_eval returns
+// BUMP_E_EXCHANGE: ranks can no longer disagree about whether an evaluation happened.
 constexpr int P2P_MAX_RANKS = 16;
 constexpr unsigned long long P2P_POISON = ~0ull;
 struct Mailbox {
-    double mail[2][P2P_MAX_RANKS][PARTIAL_LEN];
-    unsigned long long flag[2][P2P_MAX_RANKS];
+    uint4 line[2][P2P_MAX_RANKS][PARTIAL_LEN];        // {lo, epoch32, hi, epoch32}
+    unsigned long long flag[2][P2P_MAX_RANKS];        // P2P_POISON: that rank's exchange has failed
 };
 struct Peers {
     Mailbox* box[P2P_MAX_RANKS];   // box[r] = rank r's mailbox as mapped into this process (box[rank] = local)
@@ -150,39 +157,64 @@ struct Peers {
 };
 // exchange state of a context: [0] epoch of the last completed exchange, [1] broken (sticky)
 
-// Called by all threads of ONE block.  Returns STATUS_OK, STATUS_EXCHANGE_TIMEOUT (a peer never arrived) or
-// STATUS_EXCHANGE_POISONED (a peer failed, now or earlier).
-__device__ inline double p2p_exchange(const Peers& peers, const double* __restrict__ partial,
-                                      unsigned long long* __restrict__ state, int& par /* out: parity of this exchange */) {
+// Called by all threads of ONE block.  `parts` (shared memory, [nranks][PARTIAL_LEN]) holds this rank's partial in
+// its first PARTIAL_LEN entries on entry and every rank's partial in rank order on a successful return.  Returns
+// STATUS_OK, STATUS_EXCHANGE_TIMEOUT (a peer never arrived) or STATUS_EXCHANGE_POISONED (a peer failed, now or earlier).
+__device__ inline double p2p_exchange(const Peers& peers, double* parts, unsigned long long* __restrict__ state) {
     __shared__ int s_status;
     const int tid = threadIdx.x;
     const unsigned long long epoch = state[0] + 1ull;
     const bool broken = state[1] != 0ull;
-    par = (int)(epoch & 1ull);
+    const int par = (int)(epoch & 1ull);
+    const uint32_t e32 = (uint32_t)epoch;
+    const int n = peers.nranks * PARTIAL_LEN;
     if (tid == 0) s_status = broken ? 2 : 0;
-    if (!broken)
-        for (int r = 0; r < peers.nranks; ++r)
-            for (int k = tid; k < PARTIAL_LEN; k += blockDim.x) peers.box[r]->mail[par][peers.rank][k] = partial[k];
-    __threadfence_system();
-    __syncthreads();
-    if (tid < peers.nranks && !broken) {
-        *reinterpret_cast<volatile unsigned long long*>(&peers.box[tid]->flag[par][peers.rank]) = epoch;
-        const volatile unsigned long long* mine = &peers.box[peers.rank]->flag[par][tid];
-        const unsigned long long t0 = global_ns();
-        for (;;) {
-            const unsigned long long v = *mine;
-            if (v == epoch) break;
-            if (v == P2P_POISON) {
-                atomicMax(&s_status, 2);
-                break;
-            }
-            if (global_ns() - t0 > peers.timeout_ns) {   // a peer is gone: fail instead of hanging the GPU
-                atomicMax(&s_status, 1);
-                break;
-            }
+    // A peer that failed EARLIER (it timed out waiting for this rank, say) has left its poison here, but its lines of
+    // this epoch may be complete all the same - it sends before it waits.  So the poison flags are looked at whether or
+    // not the data arrives; the load is issued now and consumed after the sends.
+    unsigned long long poisoned = 0ull;
+    if (!broken && tid < peers.nranks)
+        poisoned = *reinterpret_cast<const volatile unsigned long long*>(&peers.box[peers.rank]->flag[par][tid]);
+    if (!broken) {
+        for (int idx = tid; idx < n; idx += blockDim.x) {
+            const int r = idx / PARTIAL_LEN, k = idx % PARTIAL_LEN;
+            const double v = parts[k];
+            uint4* dst = &peers.box[r]->line[par][peers.rank][k];
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((uint32_t)__double2loint(v)),
+                         "r"(e32), "r"((uint32_t)__double2hiint(v)), "r"(e32)
+                         : "memory");
         }
     }
-    __threadfence_system();
+    __syncthreads();   // every thread has read this rank's partial out of `parts`; s_status is set
+    if (poisoned == P2P_POISON) atomicMax(&s_status, 2);
+    if (!broken) {
+        const unsigned long long t0 = global_ns();
+        for (int idx = tid; idx < n; idx += blockDim.x) {
+            const int r = idx / PARTIAL_LEN, k = idx % PARTIAL_LEN;
+            const uint4* src = &peers.box[peers.rank]->line[par][r][k];
+            const volatile unsigned long long* poison = &peers.box[peers.rank]->flag[par][r];
+            uint32_t lo = 0u, e0 = 0u, hi = 0u, e1 = 0u;
+            for (unsigned int spins = 1;; ++spins) {
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo), "=r"(e0), "=r"(hi), "=r"(e1)
+                             : "l"(src)
+                             : "memory");
+                if (e0 == e32 && e1 == e32) break;
+                if ((spins & 7u) == 0u) {   // the failure checks stay off the fast path
+                    if (*reinterpret_cast<volatile int*>(&s_status) != 0) break;   // another thread has given up
+                    if (*poison == P2P_POISON) {
+                        atomicMax(&s_status, 2);
+                        break;
+                    }
+                    if (global_ns() - t0 > peers.timeout_ns) {   // a peer is gone: fail instead of hanging the GPU
+                        atomicMax(&s_status, 1);
+                        break;
+                    }
+                }
+            }
+            parts[idx] = __hiloint2double((int)hi, (int)lo);
+        }
+    }
     __syncthreads();
     const int st = s_status;
     if (st != 0) {
@@ -455,16 +487,10 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
     if (out_header) {
         int nparts = 1;
         double status = STATUS_OK;
-        if (peers) {   // multi-rank, fused exchange over peer memory
-            __threadfence();
+        if (peers) {   // multi-rank, fused exchange over peer memory: s_part <- every rank's partial
             __syncthreads();
-            int par;   // (not re-read from exchange_state: only thread 0 has written the new epoch there)
-            status = p2p_exchange(*peers, s_part, exchange_state, par);   // pushes the shared-memory copy to every peer
-            if (status == STATUS_OK) {
-                nparts = peers->nranks;
-                const double* mail = &peers->box[peers->rank]->mail[par][0][0];
-                for (int k = tid; k < nparts * PARTIAL_LEN; k += EPI_THREADS) s_part[k] = __ldcg(mail + k);
-            }
+            status = p2p_exchange(*peers, s_part, exchange_state);
+            if (status == STATUS_OK) nparts = peers->nranks;
         }
         if (tid < OUT_HEADER) s_out[tid] = 0.0;
         __syncthreads();
