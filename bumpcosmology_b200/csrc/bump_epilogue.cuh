@@ -287,7 +287,8 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
                 const double* __restrict__ blob,
                 double* __restrict__ neff_out, double* __restrict__ slots, unsigned int* __restrict__ ticket,
                 double* __restrict__ partial, double* __restrict__ out_header, const Peers* __restrict__ peers,
-                unsigned long long* __restrict__ exchange_state, unsigned long long* __restrict__ tl) {
+                unsigned long long* __restrict__ exchange_state, unsigned long long* __restrict__ tl,
+                unsigned long long* __restrict__ done_seq /* evaluations completed (host call's graph), or null */) {
     __shared__ double red[32 + (EPI_THREADS / 32) * 32];
     static_assert(32 + (EPI_THREADS / 32) * 32 >= (EPI_THREADS / 32) * (NACC + 3), "block sums fit");
     __shared__ double s_max;
@@ -510,6 +511,9 @@ epilogue_kernel(const double* __restrict__ part, const int* __restrict__ rec_off
             }
             out_header[tid] = v;
         }
+        // the host call's graph copies this counter to pinned host memory behind the result: the calling thread polls
+        // it there instead of synchronising the stream
+        if (done_seq != nullptr && tid == 0) *done_seq = *done_seq + 1ull;
     }
     timeline_end(tl, TL_EPI_LAST);
     timeline_end(tl, TL_EPILOGUE);

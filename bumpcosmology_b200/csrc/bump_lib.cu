@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -268,6 +269,10 @@ struct bump_ctx {
            *d_out = nullptr;
     unsigned int* d_ticket = nullptr;
     double *h_theta = nullptr, *h_out = nullptr;   // pinned
+    unsigned long long* h_done = nullptr;          // pinned: number of completed host-call evaluations (see bump_eval)
+    unsigned long long* d_seq = nullptr;           // ... its device-side source, bumped by the epilogue
+    unsigned long long host_seq = 0;               // host-call evaluations launched
+    cudaGraphExec_t graph_host = nullptr;          // copy in -> 3 kernels -> copy out -> copy of the counter
     int64_t out_len = OUT_HEADER;
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -294,8 +299,13 @@ int set_device(const bump_ctx* c) {
     return BUMP_OK;
 }
 
-void free_plan(bump_ctx* c) {
+void drop_graphs(bump_ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    if (c->graph_host) cudaGraphExecDestroy(c->graph_host), c->graph_host = nullptr;
+}
+
+void free_plan(bump_ctx* c) {
+    drop_graphs(c);
     cudaFree(c->d_plan_arena), c->d_plan_arena = nullptr;
     c->d_rec_off = nullptr, c->d_part = nullptr, c->d_slots = nullptr, c->d_out = nullptr;
     if (c->h_out) cudaFreeHost(c->h_out), c->h_out = nullptr;
@@ -468,7 +478,7 @@ cudaError_t launch_dependent(const bool programmatic, void (*kernel)(KArgs...), 
 // The per-rank part of one evaluation: theta -> partial (+ neff).  3 launches.
 int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, double* neff_dev, cudaStream_t s,
                    cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr, double* fused_out = nullptr,
-                   unsigned long long* tl = nullptr) {
+                   unsigned long long* tl = nullptr, const bool count = false) {
     prologue_kernel<<<PRO_BLOCKS, PRO_THREADS, 0, s>>>(theta_dev, c->d_aux, c->d_blob, c->d_cbank, c->d_ticket + 4,
                                                        consts_of(c), tl);
 #if !defined(BUMP_SCALARS_FROM_BLOB) && defined(BUMP_CBANK_COPY_NODE)
@@ -485,15 +495,17 @@ int launch_partial(bump_ctx* c, const double* theta_dev, double* partial_dev, do
     const int nb_evt = (c->work.nobs + epb - 1) / epb;
     CK(launch_dependent(PDL_EPILOGUE, epilogue_kernel, dim3(nb_evt + c->nb_sel), dim3(EPI_THREADS), 0, s, c->d_part, c->d_rec_off,
                         c->work, (double)c->sel.ncols, c->lpe, c->nb_sel, c->d_blob, neff_dev, c->d_slots,
-                        c->d_ticket + 1, partial_dev, fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl));
+                        c->d_ticket + 1, partial_dev, fused_out, fused_out ? c->d_peers : nullptr, c->d_epoch, tl,
+                        (count && fused_out) ? c->d_seq : nullptr));
     CK(cudaGetLastError());
     return BUMP_OK;
 }
 
 int launch_eval(bump_ctx* c, const double* theta_dev, double* out_dev, cudaStream_t s, cudaEvent_t k0 = nullptr,
-                cudaEvent_t k1 = nullptr, unsigned long long* tl = nullptr) {
+                cudaEvent_t k1 = nullptr, unsigned long long* tl = nullptr, const bool count = false) {
     // single rank, or peer-memory exchange: the epilogue's last block finalizes in place (3 launches per evaluation)
-    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev, tl))
+    if (int r = launch_partial(c, theta_dev, c->d_partial, out_dev + OUT_HEADER, s, k0, k1, c->comm ? nullptr : out_dev, tl,
+                               count))
         return r;
     if (c->comm) {
         NCK(g_nccl.AllGather(c->d_partial, c->d_gather, PARTIAL_LEN, NCCL_FLOAT64, c->comm, s));
@@ -583,6 +595,58 @@ int ensure_graph(bump_ctx* c) {
     return BUMP_OK;
 }
 
+// The host call as ONE graph: theta from pinned host memory, the three kernels, the result and then the counter of
+// completed evaluations to pinned host memory.  bump_eval launches it (one driver call) and polls the counter in
+// user space instead of issuing two copies, the launch and a stream synchronisation.
+int ensure_graph_host(bump_ctx* c) {
+    if (c->graph_host) return BUMP_OK;
+    const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream);
+    int r = (e == cudaSuccess) ? launch_eval(c, c->d_theta, c->d_out, c->stream, nullptr, nullptr, nullptr, true) : BUMP_OK;
+    if (e == cudaSuccess && !r)
+        e = cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * c->out_len, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && !r)
+        e = cudaMemcpyAsync(c->h_done, c->d_seq, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+    if (r) {
+        if (g) cudaGraphDestroy(g);
+        return r;
+    }
+    CK(e);
+    CK(e2);
+    CK(cudaGraphInstantiate(&c->graph_host, g, 0));
+    CK(cudaGraphDestroy(g));
+    return BUMP_OK;
+}
+bool host_graph_usable(const bump_ctx* c) {
+    static const bool on = getenv("BUMP_HOST_GRAPH") != nullptr;
+    return on && !(c->flags & BUMP_FLAG_NO_GRAPH) && !c->comm;   // (NCCL exchange: finalize_kernel writes the result)
+}
+
+// Wait until the counter in pinned host memory says that host-call evaluation `expect` is complete (spinning in user
+// space); the stream is queried now and then so that a faulted kernel ends the wait with its error.
+int wait_done(bump_ctx* c, const unsigned long long expect) {
+    const volatile unsigned long long* f = c->h_done;
+    for (unsigned int it = 1;; ++it) {
+        if (*f == expect) break;
+        if ((it & 0x1FFFu) == 0u) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*f == expect) break;
+                return fail(BUMP_E_CUDA, "evaluation finished without publishing its completion counter");
+            }
+            if (e != cudaErrorNotReady) return fail(BUMP_E_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(e));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return BUMP_OK;
+}
+
 int run_once(bump_ctx* c) {   // d_theta -> d_out on the context stream
     if (!(c->flags & BUMP_FLAG_NO_GRAPH))
         if (int r = ensure_graph(c)) return r;
@@ -641,7 +705,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         const size_t o_theta = take(sizeof(double) * NTHETA_MAX), o_aux = take(sizeof(double) * AUX_DOUBLES),
                      o_blob = take(BLOB_BYTES_MAX), o_partial = take(sizeof(double) * PARTIAL_LEN),
                      o_ticket = take(sizeof(unsigned int) * 8), o_fixed = take(sizeof(double) * NZ),
-                     o_epoch = take(2 * sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * (2 * TL_N + TL_WARP_SLOTS));
+                     o_epoch = take(2 * sizeof(unsigned long long)), o_seq = take(sizeof(unsigned long long)), o_tl = take(sizeof(unsigned long long) * (2 * TL_N + TL_WARP_SLOTS));
         CK(cudaMalloc(&c->d_arena, off));
         CK(cudaMemset(c->d_arena, 0, off));
         CK(cudaDeviceSynchronize());   // (a memset of device memory is asynchronous, and c->stream does not wait for the default stream)
@@ -654,6 +718,7 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
         c->d_fixed_tab = reinterpret_cast<double*>(base + o_fixed);
         c->d_epoch = reinterpret_cast<unsigned long long*>(base + o_epoch);
         c->d_timeline = reinterpret_cast<unsigned long long*>(base + o_tl);
+        c->d_seq = reinterpret_cast<unsigned long long*>(base + o_seq);
     }
     {   // theta-independent part of the blob: 2^(j/NEXPT), correctly rounded (x87 extended precision on the host)
         std::vector<double> expt(EXPT_DOUBLES);
@@ -663,6 +728,8 @@ int bump_ctx_create(bump_ctx** out, int device, uint32_t flags) {
     }
     // [0] unused, [1] epilogue ticket, [2] unused, [3] bad-input flag, [4] prologue ticket, [5] bad-theta flag
     CK(cudaMallocHost(&c->h_theta, sizeof(double) * NTHETA_MAX));
+    CK(cudaMallocHost(&c->h_done, 64));
+    *c->h_done = 0ull;
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     if (device < 64) {   // the least-used constant-bank slot of this device that no captured graph has pinned
@@ -730,6 +797,7 @@ void bump_ctx_destroy(bump_ctx* c) {
     c->sel.reset();
     cudaFree(c->d_gather);
     if (c->h_theta) cudaFreeHost(c->h_theta);
+    if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -789,10 +857,22 @@ int bump_eval(bump_ctx* c, const double* theta, double* out) {
     if (int r = ensure_ready(c)) return r;
     const int nth = c->use_wa ? NTHETA_MAX : NTHETA;
     memcpy(c->h_theta, theta, sizeof(double) * nth);
-    CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
-    if (int r = run_once(c)) return r;
-    CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * c->out_len, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (host_graph_usable(c)) {
+        if (int r = ensure_graph_host(c)) return r;
+        const unsigned long long expect = c->host_seq + 1ull;
+        {
+            SlotGuard chain;
+            if (int r = chain.begin(c, c->stream, true)) return r;
+            CK(cudaGraphLaunch(c->graph_host, c->stream));
+        }
+        c->host_seq = expect;
+        if (int r = wait_done(c, expect)) return r;
+    } else {
+        CK(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+        if (int r = run_once(c)) return r;
+        CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * c->out_len, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     memcpy(out, c->h_out, sizeof(double) * c->out_len);
     if (c->h_out[OUT_STATUS] != STATUS_OK)
         return fail(BUMP_E_EXCHANGE,
@@ -874,7 +954,7 @@ int bump_comm_attach(bump_ctx* c, const void* id128, int nranks, int rank) {
     c->rank = rank;
     cudaFree(c->d_gather);
     CK(cudaMalloc(&c->d_gather, sizeof(double) * PARTIAL_LEN * nranks));
-    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    drop_graphs(c);
     return BUMP_OK;
 }
 
@@ -923,7 +1003,7 @@ int bump_p2p_attach(bump_ctx* c, const void* handles, int nranks, int rank) {
     c->h_peers = p;
     c->nranks = nranks;
     c->rank = rank;
-    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    drop_graphs(c);
     return BUMP_OK;
 }
 
@@ -941,7 +1021,7 @@ int bump_p2p_detach(bump_ctx* c) {
     CK(cudaDeviceSynchronize());
     c->nranks = 1;
     c->rank = 0;
-    if (c->graph) cudaGraphExecDestroy(c->graph), c->graph = nullptr;
+    drop_graphs(c);
     return BUMP_OK;
 }
 

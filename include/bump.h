@@ -95,7 +95,8 @@ int64_t bump_out_len(const bump_ctx* ctx);
 
 /* One evaluation of the hot path (intensity_models.py:374-394,401 + its reverse pass): theta (HOST, 14 or 15
  * doubles) -> out (HOST, bump_out_len doubles).  Synchronous: copies theta in, replays the kernel graph,
- * copies the result out.  Non-finite or out-of-support theta yields NaN/-inf outputs, not an error
+ * copies the result out (environment BUMP_HOST_GRAPH=1: all of that as one graph launch, the calling thread polling
+ * a completion counter in pinned memory instead of synchronising the stream; measured equal, +2 % for four chains).  Non-finite or out-of-support theta yields NaN/-inf outputs, not an error
  * (NUTS relies on that).  If a communicator is attached, the result is the merged all-rank value, identical
  * bit for bit on every rank; neff[] stays local to the rank's events. */
 int bump_eval(bump_ctx* ctx, const double* theta, double* out);

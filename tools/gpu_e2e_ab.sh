@@ -1,11 +1,11 @@
 #!/bin/bash
-# The host call (bump_eval through Hyperlikelihood.raw) with and without the zero-copy host graph, and 4 concurrent
+# The host call (bump_eval through Hyperlikelihood.raw) with and without the one-graph host path, and 4 concurrent
 # NUTS chains on top of each (run under gpurun):  tools/gpu_e2e_ab.sh [tag]
 set -u
 out=gpurun_out; mkdir -p $out
 tag=${1:-e2e}
-for mode in copies zerocopy copies zerocopy; do
-  if [ $mode = copies ]; then export BUMP_NO_ZERO_COPY=1; else unset BUMP_NO_ZERO_COPY; fi
+for mode in calls onegraph calls onegraph; do
+  if [ $mode = calls ]; then unset BUMP_HOST_GRAPH; else export BUMP_HOST_GRAPH=1; fi
   timeout 600 python - <<PY 2>&1 | tee -a $out/${tag}_ab.txt
 import sys, time, numpy as np
 sys.path.insert(0, ".")
