@@ -117,7 +117,7 @@ constexpr int NCCL_FLOAT64 = 8;   // ncclDouble in nccl.h
 // free) makes the 32 lanes of a warp land in the same or in neighbouring records of the d_L tables and of the mass
 // table - at m1 AND at m2 = q m1: a shared-memory read of 16-byte records is conflict-free when the 8 lanes of a
 // quarter-warp hit records that are equal or less than 8 apart (DESIGN.md "sample order").
-//   key = row | d_L bucket (1/16 octave) | m1_det bucket (4 % wide) | m2_det (fine, 1/128 in log), the direction of
+//   key = row | d_L bucket (1/16 octave) | m1_det bucket (4 % wide) | m2_det (fine, 1/512 in log), the direction of
 //   the last field alternating from one m1 bucket to the next so that the walk through the (m1, m2) plane is continuous.
 // The buckets are in detector-frame quantities (theta-independent); inside one d_L bucket (1 + z) is the same for every
 // sample to a few percent whatever the cosmology, so neighbours in (m1_det, m2_det) are neighbours in the source
@@ -136,12 +136,22 @@ __global__ void locality_keys_kernel(const double* __restrict__ m1d, const doubl
 #else
         // (non-finite or non-positive inputs are rejected by prepare_columns_kernel right after; here they only
         // have to produce SOME key)
-        const unsigned int kd = ((unsigned int)__double2hiint(dl[i]) >> 16) & 0x7FFFu;        // exponent + 4 mantissa bits
+#ifndef BUMP_SORT_DL_BITS
+#define BUMP_SORT_DL_BITS 4        // mantissa bits of the d_L bucket: 1/16 octave
+#endif
+#ifndef BUMP_SORT_M1_PER_LOG
+#define BUMP_SORT_M1_PER_LOG 25.0  // m1_det buckets per unit of log: 0.04 wide
+#endif
+        static_assert(BUMP_SORT_DL_BITS >= 0 && BUMP_SORT_DL_BITS <= 8, "key layout: 27 | 11 + bits | 10 | the rest");
+        constexpr int DLB = 11 + BUMP_SORT_DL_BITS;           // bits of the d_L field
+        const unsigned int kd = ((unsigned int)__double2hiint(dl[i]) >> (20 - BUMP_SORT_DL_BITS)) & ((1u << DLB) - 1u);
         const double lm1 = log(m1d[i]), lm2 = lm1 + log(q[i]);
-        const int km = min(max((int)floor(lm1 * 25.0) + 512, 0), 1023);                       // 0.04 in log m1_det
-        int k2 = min(max((int)floor((lm2 + 8.0) * 128.0), 0), 4095);                          // 1/128 in log m2_det
-        if (km & 1) k2 = 4095 - k2;
-        keys[i] = (row << 37) | ((unsigned long long)kd << 22) | ((unsigned long long)km << 12) | (unsigned long long)k2;
+        const int km = min(max((int)floor(lm1 * BUMP_SORT_M1_PER_LOG) + 512, 0), 1023);       // 10 bits
+        constexpr int K2B = 64 - 27 - 10 - DLB;               // bits left for m2 (12 with the default d_L field)
+        constexpr int K2MAX = (1 << K2B) - 1;
+        int k2 = min(max((int)floor((lm2 + 2.0) * (double)(1 << (K2B - 3))), 0), K2MAX);      // 0.14 .. 400 Msun, clamped
+        if (km & 1) k2 = K2MAX - k2;
+        keys[i] = (row << 37) | ((unsigned long long)kd << (10 + K2B)) | ((unsigned long long)km << K2B) | (unsigned long long)k2;
 #endif
         idx[i] = (unsigned int)i;
     }
