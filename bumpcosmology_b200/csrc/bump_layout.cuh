@@ -202,8 +202,8 @@ constexpr int TL_WARP_SLOTS = 4096;   // per-warp end times of the streaming ker
 // Measured on B200 (profiles/r02_ab_experiments.md, GWTC-3 shape, same box):
 //   stream kernel -> epilogue, dependents released when the stream kernel's blocks exit (default): -0.7 us
 //   ... released when the first warp of every block is done (BUMP_PDL_EPI_TRIGGER=1):              -0.6 us
-//   ... released at kernel start (=2): +3.6 us - the waiting epilogue blocks pile up on the few SMs that have
-//       room beside a stream-kernel block instead of spreading over all of them
+//   ... released at kernel start (=2): -0.5 us or nothing where the grid leaves SMs idle for every epilogue block
+//       (GWTC-3 shape), +4 us where it does not (8-GPU shard: the waiting blocks queue up on the one idle SM)
 //   prologue -> stream kernel as well (BUMP_PDL_STREAM): nothing on top (the stream kernel needs a whole SM's shared
 //       memory, so it cannot start beside a prologue block), and with dependents released at the prologue's start
 //       concurrent contexts returned WRONG results (the stream kernel's constant-bank reads are only ordered
