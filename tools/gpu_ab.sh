@@ -18,7 +18,9 @@ for name, cat in (("gwtc3", make_catalog("gwtc3").as_args()), ("o5/8", shard_cat
     like.time_evals(THETA_DEFAULT, 30)
     n = 200 if name != "o5" else 40
     tot, ker = like.time_evals(THETA_DEFAULT, n, kernel=True)
-    row.append("%s %.2f us/eval (stream %.2f)" % (name, 1e3 * tot / n, 1e3 * ker / n))
+    import hashlib
+    digest = hashlib.md5(np.ascontiguousarray(like.raw(THETA_DEFAULT)).tobytes()).hexdigest()[:8]   # bitwise identity of builds
+    row.append("%s %.2f us/eval (stream %.2f) %s" % (name, 1e3 * tot / n, 1e3 * ker / n, digest))
     like.close()
 print(" | ".join(row), flush=True)
 PY
